@@ -1,0 +1,45 @@
+// Multi-tensor Adam (K19 of SURVEY.md): one launch updates every parameter of one optimizer.
+// Semantics = torch.optim.Adam(betas=(b1,b2), eps, weight_decay=0, amsgrad=False) as configured at
+// scripts/train_expressive.py:212-230 (lr 5e-4, betas (0.5, 0.999); discriminator lr x0.2):
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+#include "common.cuh"
+
+namespace {
+constexpr int ADAM_CHUNK = 16384;  // elements per CTA-chunk
+
+// table[k] = {p, g, m, v} device addresses of tensor k;  chunk c -> (tensor chunk_tensor[c], offset chunk_off[c])
+__global__ void __launch_bounds__(256) adam_multi_kernel(const int64_t* __restrict__ table, const int64_t* __restrict__ sizes,
+                                                         const int* __restrict__ chunk_tensor,
+                                                         const int64_t* __restrict__ chunk_off, float lr, float b1, float b2,
+                                                         float eps, float bc1, float bc2_sqrt) {
+    const int k = chunk_tensor[blockIdx.x];
+    const int64_t off = chunk_off[blockIdx.x];
+    float* __restrict__ p = reinterpret_cast<float*>(table[4 * k + 0]);
+    const float* __restrict__ g = reinterpret_cast<const float*>(table[4 * k + 1]);
+    float* __restrict__ m = reinterpret_cast<float*>(table[4 * k + 2]);
+    float* __restrict__ v = reinterpret_cast<float*>(table[4 * k + 3]);
+    const int64_t n = sizes[k];
+    const int64_t end = min(n, off + ADAM_CHUNK);
+    const float step_size = lr / bc1;
+    for (int64_t i = off + threadIdx.x; i < end; i += blockDim.x) {
+        float gi = g[i];
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= step_size * (mi / denom);
+    }
+}
+}  // namespace
+
+// table: [ntensors*4] int64 device addresses (p,g,m,v), sizes: [ntensors] int64, chunk maps built by the host
+// (chunk = 16384 elements).  step = the (1-based) step count AFTER increment, shared by all tensors.
+HA2G_API int ha2g_adam_multi(const int64_t* table, const int64_t* sizes, const int* chunk_tensor, const int64_t* chunk_off,
+                             int nchunks, float lr, float b1, float b2, float eps, int step, cudaStream_t stream) {
+    if (nchunks <= 0) return 0;
+    const double bc1 = 1.0 - pow((double)b1, (double)step);
+    const double bc2 = 1.0 - pow((double)b2, (double)step);
+    adam_multi_kernel<<<nchunks, 256, 0, stream>>>(table, sizes, chunk_tensor, chunk_off, lr, b1, b2, eps, (float)bc1,
+                                                   (float)sqrt(bc2));
+    HA2G_RETURN_LAST();
+}

@@ -1,0 +1,288 @@
+// Audio-encoder kernels that are not convolutions (K4, K5, K6 of SURVEY.md), all NHWC / channels-last:
+//   * squeeze-excite block tail  (ResNetBlocks.py:29-37,81-96): GAP -> FC -> ReLU -> FC -> sigmoid ->
+//     channel scale -> + residual -> ReLU, forward and backward
+//   * PixelShuffle (ResNetSE34V2.py:165-166,177-178) and the head flatten
+//     (B,C,F,T).reshape(B,C*F,T).transpose(1,2) (ResNetSE34V2.py:160-162) as index remaps
+//   * speaker-conditioned softmax blend of the three feature levels (ResNetSE34V2.py:202-212)
+#include "common.cuh"
+
+namespace {
+
+// ---- SE -------------------------------------------------------------------------------------------
+// gap[n,c] = mean_hw u[n,hw,c].   grid (C/32, N), block (32, 8)
+__global__ void se_gap_kernel(const float* __restrict__ u, float* __restrict__ gap, int HW, int C) {
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int n = blockIdx.y;
+    float s = 0.f;
+    if (c < C) {
+        const float* base = u + (size_t)n * HW * C + c;
+        for (int p = threadIdx.y; p < HW; p += 8) s += base[(size_t)p * C];
+    }
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+        gap[(size_t)n * C + c] = t / (float)HW;
+    }
+}
+
+// per sample: h = relu(W1 gap + b1) [R];  s = sigmoid(W2 h + b2) [C].   grid N, block C (<= 256)
+__global__ void se_fc_fwd_kernel(const float* __restrict__ gap, const float* __restrict__ w1, const float* __restrict__ b1,
+                                 const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ hbuf,
+                                 float* __restrict__ sbuf, int C, int R) {
+    __shared__ float g[256];
+    __shared__ float h[32];
+    const int n = blockIdx.x, t = threadIdx.x;
+    if (t < C) g[t] = gap[(size_t)n * C + t];
+    __syncthreads();
+    if (t < R) {
+        float a = b1[t];
+        for (int c = 0; c < C; ++c) a = fmaf(w1[t * C + c], g[c], a);
+        a = fmaxf(a, 0.f);
+        h[t] = a;
+        hbuf[(size_t)n * R + t] = a;
+    }
+    __syncthreads();
+    if (t < C) {
+        float a = b2[t];
+        for (int r = 0; r < R; ++r) a = fmaf(w2[t * R + r], h[r], a);
+        sbuf[(size_t)n * C + t] = ha2g_sigmoid(a);
+    }
+}
+
+// out = relu(u * s[n,c] + res)
+__global__ void se_apply_kernel(const float* __restrict__ u, const float* __restrict__ s, const float* __restrict__ res,
+                                float* __restrict__ out, int64_t total, int HW, int C) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int64_t n = i / ((int64_t)HW * C);
+        out[i] = fmaxf(fmaf(u[i], s[n * C + c], res[i]), 0.f);
+    }
+}
+
+// g = dout * (out > 0);  dres = g;  ds[n,c] = sum_hw g * u.     grid (C/32, N), block (32, 8)
+__global__ void se_bwd_a_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ u,
+                                float* __restrict__ dres, float* __restrict__ ds, int HW, int C) {
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int n = blockIdx.y;
+    float s = 0.f;
+    if (c < C) {
+        const size_t base = (size_t)n * HW * C + c;
+        for (int p = threadIdx.y; p < HW; p += 8) {
+            size_t i = base + (size_t)p * C;
+            float g = out[i] > 0.f ? dout[i] : 0.f;
+            dres[i] = g;
+            s = fmaf(g, u[i], s);
+        }
+    }
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+        ds[(size_t)n * C + c] = t;
+    }
+}
+
+// per sample FC backward; weight/bias grads accumulated with atomics.  grid N, block C
+__global__ void se_fc_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ sbuf, const float* __restrict__ hbuf,
+                                 const float* __restrict__ gap, const float* __restrict__ w1, const float* __restrict__ w2,
+                                 float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
+                                 float* __restrict__ db2, float* __restrict__ dgap, int C, int R) {
+    __shared__ float dz2[256];
+    __shared__ float dz1[32];
+    __shared__ float h[32];
+    __shared__ float g[256];
+    const int n = blockIdx.x, t = threadIdx.x;
+    if (t < R) h[t] = hbuf[(size_t)n * R + t];
+    if (t < C) {
+        float s = sbuf[(size_t)n * C + t];
+        dz2[t] = ds[(size_t)n * C + t] * s * (1.f - s);
+        g[t] = gap[(size_t)n * C + t];
+    }
+    __syncthreads();
+    if (t < C) {
+        atomicAdd(db2 + t, dz2[t]);
+        for (int r = 0; r < R; ++r) atomicAdd(dw2 + t * R + r, dz2[t] * h[r]);
+    }
+    if (t < R) {
+        float a = 0.f;
+        for (int c = 0; c < C; ++c) a = fmaf(w2[c * R + t], dz2[c], a);
+        a = h[t] > 0.f ? a : 0.f;
+        dz1[t] = a;
+        atomicAdd(db1 + t, a);
+    }
+    __syncthreads();
+    if (t < C) {
+        float a = 0.f;
+        for (int r = 0; r < R; ++r) {
+            a = fmaf(w1[r * C + t], dz1[r], a);
+            atomicAdd(dw1 + r * C + t, dz1[r] * g[t]);
+        }
+        dgap[(size_t)n * C + t] = a;
+    }
+}
+
+// du = (dout * (out>0)) * s[n,c] + dgap[n,c] / HW
+__global__ void se_bwd_b_kernel(const float* __restrict__ dres /* = dout*(out>0) */, const float* __restrict__ s,
+                                const float* __restrict__ dgap, float* __restrict__ du, int64_t total, int HW, int C) {
+    const float inv = 1.f / (float)HW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int64_t n = i / ((int64_t)HW * C);
+        du[i] = fmaf(dres[i], s[n * C + c], dgap[n * C + c] * inv);
+    }
+}
+
+// ---- index remaps -------------------------------------------------------------------------------------
+// PixelShuffle(r), NHWC:  out[n, h*r+i, w*r+j, c] = in[n, h, w, c*r*r + i*r + j].   inverse: swap roles.
+__global__ void pixel_shuffle_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t N, int H, int W, int Cout,
+                                     int r, int inverse) {
+    const int Ho = H * r, Wo = W * r;
+    const int64_t total = N * Ho * Wo * Cout;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(e % Cout);
+        int64_t p = e / Cout;
+        int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho);
+        int64_t n = p / ((int64_t)Wo * Ho);
+        int h = ho / r, i = ho % r, w = wo / r, j = wo % r;
+        int64_t in_idx = ((n * H + h) * W + w) * ((int64_t)Cout * r * r) + (int64_t)c * r * r + i * r + j;
+        if (inverse) dst[in_idx] = src[e]; else dst[e] = src[in_idx];
+    }
+}
+// head flatten: dst[n][t][c*F + f] = src[n][f][t][c]   (src NHWC with H=F, W=T).  inverse: swap roles.
+__global__ void head_flatten_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t N, int F, int T, int C,
+                                    int inverse) {
+    const int64_t total = N * F * T * C;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        // e indexes the flattened side [n][t][c*F+f]
+        int f = (int)(e % F);
+        int c = (int)((e / F) % C);
+        int t = (int)((e / ((int64_t)F * C)) % T);
+        int64_t n = e / ((int64_t)F * C * T);
+        int64_t s = ((n * F + f) * T + t) * C + c;
+        if (inverse) dst[s] = src[e]; else dst[e] = src[s];
+    }
+}
+
+// ---- speaker blend ------------------------------------------------------------------------------------
+// logits [B,3,L] -> weight = softmax over dim 1;  blend[i][b,t,:] = sum_k weight[b,k,i] * feat_k[b,t,:]
+__global__ void blend_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ f0, const float* __restrict__ f1,
+                                 const float* __restrict__ f2, float* __restrict__ weight, float* __restrict__ blend, int B,
+                                 int TC, int L) {
+    __shared__ float w[3 * 8];
+    const int b = blockIdx.x;
+    if (threadIdx.x < L) {
+        int i = threadIdx.x;
+        float a0 = logits[(b * 3 + 0) * L + i], a1 = logits[(b * 3 + 1) * L + i], a2 = logits[(b * 3 + 2) * L + i];
+        float m = fmaxf(a0, fmaxf(a1, a2));
+        float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
+        float inv = 1.f / (e0 + e1 + e2);
+        w[0 * L + i] = e0 * inv; w[1 * L + i] = e1 * inv; w[2 * L + i] = e2 * inv;
+        weight[(b * 3 + 0) * L + i] = e0 * inv;
+        weight[(b * 3 + 1) * L + i] = e1 * inv;
+        weight[(b * 3 + 2) * L + i] = e2 * inv;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < TC; e += blockDim.x) {
+        size_t idx = (size_t)b * TC + e;
+        float x0 = f0[idx], x1 = f1[idx], x2 = f2[idx];
+        for (int i = 0; i < L; ++i)
+            blend[((size_t)i * B + b) * TC + e] = x0 * w[i] + x1 * w[L + i] + x2 * w[2 * L + i];
+    }
+}
+// dfeat_k[b,t,:] = sum_i weight[b,k,i]*dblend[i][b,t,:];  dlogits via softmax backward with
+// dW[b,k,i] = dweight[b,k,i] + sum_{t,c} dblend[i][b,t,c]*feat_k[b,t,c]
+__global__ void blend_bwd_kernel(const float* __restrict__ weight, const float* __restrict__ f0, const float* __restrict__ f1,
+                                 const float* __restrict__ f2, const float* __restrict__ dweight /* may be null */,
+                                 const float* __restrict__ dblend, float* __restrict__ df0, float* __restrict__ df1,
+                                 float* __restrict__ df2, float* __restrict__ dlogits, int B, int TC, int L) {
+    __shared__ float w[24];
+    __shared__ float dwacc[24];
+    __shared__ float sh[33];
+    const int b = blockIdx.x;
+    if (threadIdx.x < 3 * L) w[threadIdx.x] = weight[b * 3 * L + threadIdx.x];
+    __syncthreads();
+    float part[24];
+    for (int q = 0; q < 3 * L; ++q) part[q] = 0.f;
+    for (int e = threadIdx.x; e < TC; e += blockDim.x) {
+        size_t idx = (size_t)b * TC + e;
+        float x0 = f0[idx], x1 = f1[idx], x2 = f2[idx];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int i = 0; i < L; ++i) {
+            float d = dblend[((size_t)i * B + b) * TC + e];
+            a0 = fmaf(w[i], d, a0); a1 = fmaf(w[L + i], d, a1); a2 = fmaf(w[2 * L + i], d, a2);
+            part[i] = fmaf(d, x0, part[i]); part[L + i] = fmaf(d, x1, part[L + i]); part[2 * L + i] = fmaf(d, x2, part[2 * L + i]);
+        }
+        df0[idx] = a0; df1[idx] = a1; df2[idx] = a2;
+    }
+    for (int q = 0; q < 3 * L; ++q) {
+        float t = block_sum(part[q], sh);
+        if (threadIdx.x == 0) dwacc[q] = t + (dweight != nullptr ? dweight[b * 3 * L + q] : 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < L) {
+        int i = threadIdx.x;
+        float dot = w[i] * dwacc[i] + w[L + i] * dwacc[L + i] + w[2 * L + i] * dwacc[2 * L + i];
+        for (int k = 0; k < 3; ++k) dlogits[(b * 3 + k) * L + i] = w[k * L + i] * (dwacc[k * L + i] - dot);
+    }
+}
+
+}  // namespace
+
+// SE tail forward.  u, res, out: [N,HW,C];  gap, s: [N,C];  h: [N,R]  (R = C/8);  C <= 256, R <= 32.
+HA2G_API int ha2g_se_fwd(const float* u, const float* res, const float* w1, const float* b1, const float* w2,
+                         const float* b2, float* gap, float* h, float* s, float* out, int N, int HW, int C, int R,
+                         cudaStream_t stream) {
+    if (C > 256 || R > 32) return (int)cudaErrorInvalidValue;
+    se_gap_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(u, gap, HW, C);
+    se_fc_fwd_kernel<<<N, 256, 0, stream>>>(gap, w1, b1, w2, b2, h, s, C, R);
+    int64_t total = (int64_t)N * HW * C;
+    se_apply_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(u, s, res, out, total, HW, C);
+    HA2G_RETURN_LAST();
+}
+// SE tail backward.  dres (= dout*(out>0)) and du are outputs [N,HW,C]; dw1,db1,dw2,db2 ACCUMULATED; ds,dgap scratch [N,C].
+HA2G_API int ha2g_se_bwd(const float* dout, const float* out, const float* u, const float* gap, const float* h,
+                         const float* s, const float* w1, const float* w2, float* dres, float* du, float* ds, float* dgap,
+                         float* dw1, float* db1, float* dw2, float* db2, int N, int HW, int C, int R,
+                         cudaStream_t stream) {
+    if (C > 256 || R > 32) return (int)cudaErrorInvalidValue;
+    se_bwd_a_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(dout, out, u, dres, ds, HW, C);
+    se_fc_bwd_kernel<<<N, 256, 0, stream>>>(ds, s, h, gap, w1, w2, dw1, db1, dw2, db2, dgap, C, R);
+    int64_t total = (int64_t)N * HW * C;
+    se_bwd_b_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(dres, s, dgap, du, total, HW, C);
+    HA2G_RETURN_LAST();
+}
+// nn.PixelShuffle(r) on NHWC: src [N,H,W,Cout*r*r] -> dst [N,H*r,W*r,Cout]  (inverse != 0: the other way)
+HA2G_API int ha2g_pixel_shuffle(const float* src, float* dst, int64_t N, int H, int W, int Cout, int r, int inverse,
+                                cudaStream_t stream) {
+    int64_t total = N * H * r * W * r * Cout;
+    pixel_shuffle_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(src, dst, N, H, W, Cout, r, inverse);
+    HA2G_RETURN_LAST();
+}
+// src [N,F,T,C] (NHWC) -> dst [N,T,C*F]  (feature index c*F+f, ResNetSE34V2.py:160-162); inverse != 0: back
+HA2G_API int ha2g_head_flatten(const float* src, float* dst, int64_t N, int F, int T, int C, int inverse,
+                               cudaStream_t stream) {
+    int64_t total = N * F * T * C;
+    head_flatten_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(src, dst, N, F, T, C, inverse);
+    HA2G_RETURN_LAST();
+}
+// speaker blend forward: logits [B,3,L], f* [B,TC] -> weight [B,3,L], blend [L,B,TC]   (L <= 8)
+HA2G_API int ha2g_blend_fwd(const float* logits, const float* f0, const float* f1, const float* f2, float* weight,
+                            float* blend, int B, int TC, int L, cudaStream_t stream) {
+    if (L > 8) return (int)cudaErrorInvalidValue;
+    blend_fwd_kernel<<<B, 256, 0, stream>>>(logits, f0, f1, f2, weight, blend, B, TC, L);
+    HA2G_RETURN_LAST();
+}
+HA2G_API int ha2g_blend_bwd(const float* weight, const float* f0, const float* f1, const float* f2, const float* dweight,
+                            const float* dblend, float* df0, float* df1, float* df2, float* dlogits, int B, int TC, int L,
+                            cudaStream_t stream) {
+    if (L > 8) return (int)cudaErrorInvalidValue;
+    blend_bwd_kernel<<<B, 256, 0, stream>>>(weight, f0, f1, f2, dweight, dblend, df0, df1, df2, dlogits, B, TC, L);
+    HA2G_RETURN_LAST();
+}

@@ -1,0 +1,191 @@
+// Train/eval BatchNorm over a [rows, C] channels-last matrix (BatchNorm2d on NHWC maps, BatchNorm1d on
+// [B*T, C] sequences) with the reference's op orderings fused in:
+//   pre_relu = 1 :  y = BN(ReLU(x))          conv -> ReLU -> BN  (ResNetBlocks.py:24-26, ResNetSE34V2.py:127-129,157-159)
+//   post_act     :  y = act(BN(x))           BN -> LeakyReLU     (hierarchy_net.py:205-210)
+// Statistics are accumulated in double (sum, sum of squares) so E[x^2]-E[x]^2 is safe for the
+// [-80,0] dB spectrogram stem.  HBM-bound: x is read once for stats and once for apply.
+#include "common.cuh"
+
+namespace {
+
+// partial column sums of f(x) and f(x)^2;  blockDim = (32, 8)
+__global__ void bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C, int pre_relu,
+                                double* __restrict__ sums /* [2][C] */, int rows_per_cta) {
+    __shared__ double sh[2][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    float s = 0.f, q = 0.f;
+    double ds = 0.0, dq = 0.0;
+    if (c < C) {
+        int cnt = 0;
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+            float v = x[r * C + c];
+            if (pre_relu) v = fmaxf(v, 0.f);
+            s += v; q += v * v;
+            if (++cnt == 64) { ds += s; dq += q; s = 0.f; q = 0.f; cnt = 0; }
+        }
+        ds += s; dq += q;
+    }
+    sh[0][threadIdx.y][threadIdx.x] = ds;
+    sh[1][threadIdx.y][threadIdx.x] = dq;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += sh[0][i][threadIdx.x]; b += sh[1][i][threadIdx.x]; }
+        atomicAdd(sums + c, a);
+        atomicAdd(sums + C + c, b);
+    }
+}
+
+// mean / invstd from the sums; running-stat update (momentum, unbiased var) as nn.BatchNorm does in train mode
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t rows, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double m = sums[c] / (double)rows;
+    double var = sums[C + c] / (double)rows - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {
+        double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var, int C,
+                                     float eps, float* __restrict__ mean, float* __restrict__ invstd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = running_mean[c];
+    invstd[c] = 1.0f / sqrtf(running_var[c] + eps);
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, int64_t n, int C, int pre_relu, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int post_act, float* __restrict__ y) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        float v = x[i];
+        if (pre_relu) v = fmaxf(v, 0.f);
+        v = (v - mean[c]) * invstd[c] * gamma[c] + beta[c];
+        y[i] = ha2g_act(v, post_act);
+    }
+}
+
+// pass 1 of backward: dbeta[c] = sum g, dgamma[c] = sum g * xhat   with g = dy * post_act'(y)
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                                     int64_t rows, int C, int pre_relu, int post_act, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, double* __restrict__ sums /* [2][C] */,
+                                     int rows_per_cta) {
+    __shared__ double sh[2][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    double ds = 0.0, dq = 0.0;
+    if (c < C) {
+        float s = 0.f, q = 0.f;
+        int cnt = 0;
+        const float mu = mean[c], is = invstd[c];
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+            float g = dy[r * C + c];
+            if (post_act) g *= ha2g_act_grad_from_out(y[r * C + c], post_act);
+            float v = x[r * C + c];
+            if (pre_relu) v = fmaxf(v, 0.f);
+            s += g; q += g * (v - mu) * is;
+            if (++cnt == 64) { ds += s; dq += q; s = 0.f; q = 0.f; cnt = 0; }
+        }
+        ds += s; dq += q;
+    }
+    sh[0][threadIdx.y][threadIdx.x] = ds;
+    sh[1][threadIdx.y][threadIdx.x] = dq;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += sh[0][i][threadIdx.x]; b += sh[1][i][threadIdx.x]; }
+        atomicAdd(sums + c, a);
+        atomicAdd(sums + C + c, b);
+    }
+}
+
+// pass 2: dx = gamma*invstd*(g - dbeta/R - xhat*dgamma/R) [* (x>0) if pre_relu];  dgamma/dbeta (+=) written by block 0
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                                    int64_t rows, int C, int pre_relu, int post_act, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+    const int64_t n = rows * C;
+    const double invR = 1.0 / (double)rows;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        float g = dy[i];
+        if (post_act) g *= ha2g_act_grad_from_out(y[i], post_act);
+        float xv = x[i];
+        float mask = 1.f;
+        if (pre_relu) { mask = xv > 0.f ? 1.f : 0.f; xv = fmaxf(xv, 0.f); }
+        float xhat = (xv - mean[c]) * invstd[c];
+        float db = (float)(sums[c] * invR), dg = (float)(sums[C + c] * invR);
+        dx[i] = gamma[c] * invstd[c] * (g - db - xhat * dg) * mask;
+    }
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            dbeta[c] += (float)sums[c];
+            dgamma[c] += (float)sums[C + c];
+        }
+    }
+}
+
+static inline void bn_grid(int64_t rows, int C, dim3& grid, int& rows_per) {
+    int gx = ha2g_div_up(C, 32);
+    int want_y = ha2g_div_up(148 * 4, gx);
+    int64_t rp = (rows + want_y - 1) / want_y;
+    if (rp < 64) rp = 64;
+    rows_per = (int)rp;
+    grid = dim3(gx, ha2g_div_up(rows, rp));
+}
+
+}  // namespace
+
+// Forward.  training != 0: batch statistics (+ running-stat update when running_mean != nullptr);
+// training == 0: running statistics.  mean/invstd [C] are outputs (saved for backward);
+// sums_scratch: 2*C doubles.  y may alias x only when pre_relu == 0 and no backward is needed.
+HA2G_API int ha2g_bn_fwd(const float* x, int64_t rows, int C, int pre_relu, int post_act, int training,
+                         const float* gamma, const float* beta, float* running_mean, float* running_var, float eps,
+                         float momentum, float* mean, float* invstd, double* sums_scratch, float* y, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    if (training) {
+        cudaError_t ce = cudaMemsetAsync(sums_scratch, 0, sizeof(double) * 2 * C, stream);
+        if (ce != cudaSuccess) return (int)ce;
+        dim3 grid; int rows_per;
+        bn_grid(rows, C, grid, rows_per);
+        bn_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, C, pre_relu, sums_scratch, rows_per);
+        bn_finalize_kernel<<<ha2g_div_up(C, 128), 128, 0, stream>>>(sums_scratch, rows, C, eps, momentum, mean, invstd,
+                                                                    running_mean, running_var);
+    } else {
+        bn_eval_stats_kernel<<<ha2g_div_up(C, 128), 128, 0, stream>>>(running_mean, running_var, C, eps, mean, invstd);
+    }
+    const int64_t n = rows * C;
+    bn_apply_kernel<<<ha2g_ew_grid(n), 256, 0, stream>>>(x, n, C, pre_relu, mean, invstd, gamma, beta, post_act, y);
+    HA2G_RETURN_LAST();
+}
+
+// Backward of the training-mode forward.  dgamma/dbeta are ACCUMULATED (+=).  y is only read when post_act != 0.
+HA2G_API int ha2g_bn_bwd(const float* dy, const float* x, const float* y, int64_t rows, int C, int pre_relu, int post_act,
+                         const float* gamma, const float* mean, const float* invstd, double* sums_scratch, float* dx,
+                         float* dgamma, float* dbeta, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    cudaError_t ce = cudaMemsetAsync(sums_scratch, 0, sizeof(double) * 2 * C, stream);
+    if (ce != cudaSuccess) return (int)ce;
+    dim3 grid; int rows_per;
+    bn_grid(rows, C, grid, rows_per);
+    bn_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd,
+                                                           sums_scratch, rows_per);
+    bn_bwd_apply_kernel<<<ha2g_ew_grid(rows * C), 256, 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd,
+                                                                    gamma, sums_scratch, dx, dgamma, dbeta);
+    HA2G_RETURN_LAST();
+}

@@ -1,0 +1,365 @@
+// HBM-bound glue kernels of the HA2G step: activations, column-block copies (concat / split /
+// broadcast), embedding gather + scatter-add, reparameterize, TCN weight-norm and causal shift,
+// cascade pre_seq build.  All are grid-stride, coalesced along the innermost (channel) axis.
+#include "common.cuh"
+
+namespace {
+
+__global__ void col_sum_kernel(const float* __restrict__ x, int rows, int cols, int ld, float* __restrict__ out,
+                               int rows_per_cta) {
+    // blockDim = (32, 8): 32 columns x 8 row lanes
+    __shared__ float sh[8][33];
+    int c = blockIdx.x * 32 + threadIdx.x;
+    int r0 = blockIdx.y * rows_per_cta;
+    int r1 = min(rows, r0 + rows_per_cta);
+    float s = 0.f;
+    if (c < cols)
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) s += x[(size_t)r * ld + c];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int act) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = ha2g_act(x[i], act);
+}
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                               int64_t n, int act) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dx[i] = dy[i] * ha2g_act_grad_from_out(y[i], act);
+}
+// y = act(a + b)
+__global__ void add_act_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                   int64_t n, int act) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = ha2g_act(a[i] + b[i], act);
+}
+// out = alpha * a + beta * b  (b may be nullptr)
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                             int64_t n, float alpha, float beta) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = alpha * a[i] + (b != nullptr ? beta * b[i] : 0.f);
+}
+// y = x * mask * scale   (dropout forward and backward)
+__global__ void mul_mask_kernel(const float* __restrict__ x, const float* __restrict__ mask, float scale,
+                                float* __restrict__ y, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = x[i] * mask[i] * scale;
+}
+
+__global__ void embedding_fwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
+                                     float* __restrict__ out, int64_t n_idx, int dim) {
+    const int64_t n = n_idx * dim;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / dim;
+        int c = (int)(i % dim);
+        out[i] = table[idx[r] * dim + c];
+    }
+}
+__global__ void embedding_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ idx,
+                                     float* __restrict__ dtable, int64_t n_idx, int dim) {
+    const int64_t n = n_idx * dim;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / dim;
+        int c = (int)(i % dim);
+        atomicAdd(dtable + idx[r] * dim + c, dout[i]);
+    }
+}
+
+// dst[(r / dst_div) * dst_ld + dst_off + c] (op)= src[(r / src_div) * src_ld + src_off + c]
+__global__ void copy_cols_kernel(const float* __restrict__ src, int src_ld, int src_off, int src_div,
+                                 float* __restrict__ dst, int dst_ld, int dst_off, int dst_div, int64_t rows, int ncols,
+                                 int mode) {
+    const int64_t n = rows * ncols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ncols;
+        int c = (int)(i % ncols);
+        float v = src[(r / src_div) * src_ld + src_off + c];
+        float* d = dst + (r / dst_div) * dst_ld + dst_off + c;
+        if (mode == 0) *d = v;
+        else if (mode == 1) *d += v;
+        else atomicAdd(d, v);
+    }
+}
+
+__global__ void gather_cols_kernel(const float* __restrict__ src, int src_ld, const int* __restrict__ idx, int n_idx,
+                                   float* __restrict__ dst, int dst_ld, int64_t rows) {
+    const int64_t n = rows * n_idx;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / n_idx;
+        int c = (int)(i % n_idx);
+        dst[r * dst_ld + c] = src[r * src_ld + idx[c]];
+    }
+}
+
+__global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                   const float* __restrict__ eps, float* __restrict__ z, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        z[i] = mu[i] + eps[i] * expf(0.5f * logvar[i]);
+}
+__global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ logvar,
+                                   const float* __restrict__ eps, float* __restrict__ dmu, float* __restrict__ dlogvar,
+                                   int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        dmu[i] = dz[i];
+        dlogvar[i] = dz[i] * eps[i] * 0.5f * expf(0.5f * logvar[i]);
+    }
+}
+
+// weight_norm (dim=0) of a Conv1d weight v[O][I][Kw] -> wcat[O][Kw*I] with wcat[o][k*I+i] = g[o]*v[o][i][k]/||v[o]||
+__global__ void tcn_weight_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, float* __restrict__ wcat,
+                                      float* __restrict__ norm_out, int I, int Kw) {
+    __shared__ float sh[33];
+    const int o = blockIdx.x;
+    const int n = I * Kw;
+    const float* vo = v + (size_t)o * n;
+    float s = 0.f;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) s += vo[e] * vo[e];
+    s = block_sum(s, sh);
+    const float nrm = sqrtf(s);
+    if (threadIdx.x == 0) norm_out[o] = nrm;
+    const float sc = g[o] / nrm;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        int i = e / Kw, k = e % Kw;
+        wcat[(size_t)o * n + k * I + i] = vo[e] * sc;
+    }
+}
+// dg[o] += sum(dW*v)/||v||;  dv[o] += g/||v|| * (dW - (sum(dW*v)/||v||^2) * v)
+__global__ void tcn_weight_bwd_kernel(const float* __restrict__ dwcat, const float* __restrict__ g,
+                                      const float* __restrict__ v, const float* __restrict__ norm,
+                                      float* __restrict__ dg, float* __restrict__ dv, int I, int Kw) {
+    __shared__ float sh[33];
+    const int o = blockIdx.x;
+    const int n = I * Kw;
+    const float* vo = v + (size_t)o * n;
+    float s = 0.f;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        int i = e / Kw, k = e % Kw;
+        s += dwcat[(size_t)o * n + k * I + i] * vo[e];
+    }
+    s = block_sum(s, sh);
+    const float nrm = norm[o];
+    if (threadIdx.x == 0) dg[o] += s / nrm;
+    const float a = g[o] / nrm, bcoef = s / (nrm * nrm);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        int i = e / Kw, k = e % Kw;
+        dv[(size_t)o * n + e] += a * (dwcat[(size_t)o * n + k * I + i] - bcoef * vo[e]);
+    }
+}
+
+// out[b,t] = [ x[b,t-d] (zeros when t<d) | x[b,t] ]      x [B,T,C] -> out [B,T,2C]
+__global__ void shift_concat_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t B, int T, int C,
+                                        int d) {
+    const int64_t n = B * T * 2 * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c2 = (int)(i % (2 * C));
+        int64_t bt = i / (2 * C);
+        int t = (int)(bt % T);
+        float v;
+        if (c2 < C) v = t >= d ? x[(bt - d) * C + c2] : 0.f;
+        else v = x[bt * C + (c2 - C)];
+        out[i] = v;
+    }
+}
+// dx[b,t] = dout[b,t][C:2C] + (t+d < T ? dout[b,t+d][0:C] : 0)
+__global__ void shift_concat_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int64_t B, int T, int C,
+                                        int d) {
+    const int64_t n = B * T * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int64_t bt = i / C;
+        int t = (int)(bt % T);
+        float v = dout[bt * 2 * C + C + c];
+        if (t + d < T) v += dout[(bt + d) * 2 * C + c];
+        dx[i] = v;
+    }
+}
+
+// cascade glue (train_hierarchy_expressive.py:252-262): pre[b,t,:] for one level.
+//   t <  n_pre: pre[.., :d] = target_k, flag = 1
+//   t >= n_pre: pre[.., dst_idx[i]] = prev_out[.., src_idx[i]], everything else 0
+__global__ void pre_seq_fwd_kernel(const float* __restrict__ target_k, const float* __restrict__ prev_out, int dp,
+                                   const int* __restrict__ slot_src /* [d+1]: src col in prev_out or -1 */,
+                                   float* __restrict__ pre, int64_t B, int T, int d, int n_pre) {
+    const int w = d + 1;
+    const int64_t n = B * T * w;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % w);
+        int64_t bt = i / w;
+        int t = (int)(bt % T);
+        float v = 0.f;
+        if (t < n_pre) v = c < d ? target_k[bt * d + c] : 1.f;
+        else if (prev_out != nullptr) {
+            int s = slot_src[c];
+            if (s >= 0) v = prev_out[bt * dp + s];
+        }
+        pre[i] = v;
+    }
+}
+// dprev[b,t,s] = (t >= n_pre && src_slot[s] >= 0) ? dpre[b,t,src_slot[s]] : 0     (overwrites dprev)
+__global__ void pre_seq_bwd_kernel(const float* __restrict__ dpre, int w,
+                                   const int* __restrict__ src_slot /* [dp]: dst col in pre or -1 */,
+                                   float* __restrict__ dprev, int64_t B, int T, int dp, int n_pre) {
+    const int64_t n = B * T * dp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int s = (int)(i % dp);
+        int64_t bt = i / dp;
+        int t = (int)(bt % T);
+        float v = 0.f;
+        if (t >= n_pre) {
+            int c = src_slot[s];
+            if (c >= 0) v = dpre[bt * w + c];
+        }
+        dprev[i] = v;
+    }
+}
+
+}  // namespace
+
+#define EW_LAUNCH(kern, n, ...) \
+    do { if ((n) > 0) kern<<<ha2g_ew_grid((n)), 256, 0, stream>>>(__VA_ARGS__); HA2G_RETURN_LAST(); } while (0)
+
+// out[c] += sum_r x[r*ld + c]   (out must be initialised by the caller; atomics across row chunks)
+HA2G_API int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    int gx = ha2g_div_up(cols, 32);
+    int want_y = ha2g_div_up(148 * 4, gx);
+    int rows_per = ha2g_div_up(rows, want_y);
+    if (rows_per < 64) rows_per = 64;
+    dim3 grid(gx, ha2g_div_up(rows, rows_per));
+    col_sum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, cols, ld, out, rows_per);
+    HA2G_RETURN_LAST();
+}
+HA2G_API int ha2g_act_fwd(const float* x, float* y, int64_t n, int act, cudaStream_t stream) {
+    EW_LAUNCH(act_fwd_kernel, n, x, y, n, act);
+}
+HA2G_API int ha2g_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, cudaStream_t stream) {
+    EW_LAUNCH(act_bwd_kernel, n, dy, y, dx, n, act);
+}
+HA2G_API int ha2g_add_act_fwd(const float* a, const float* b, float* y, int64_t n, int act, cudaStream_t stream) {
+    EW_LAUNCH(add_act_fwd_kernel, n, a, b, y, n, act);
+}
+HA2G_API int ha2g_axpby(const float* a, const float* b, float* out, int64_t n, float alpha, float beta,
+                        cudaStream_t stream) {
+    EW_LAUNCH(axpby_kernel, n, a, b, out, n, alpha, beta);
+}
+HA2G_API int ha2g_mul_mask(const float* x, const float* mask, float scale, float* y, int64_t n, cudaStream_t stream) {
+    EW_LAUNCH(mul_mask_kernel, n, x, mask, scale, y, n);
+}
+// out[r,:] = table[idx[r],:]      (nn.Embedding forward, hierarchy_net.py:49,80,117)
+HA2G_API int ha2g_embedding_fwd(const float* table, const int64_t* idx, float* out, int64_t n_idx, int dim,
+                                cudaStream_t stream) {
+    EW_LAUNCH(embedding_fwd_kernel, n_idx * dim, table, idx, out, n_idx, dim);
+}
+// dtable[idx[r],:] += dout[r,:]   (dense gradient like nn.Embedding(sparse=False))
+HA2G_API int ha2g_embedding_bwd(const float* dout, const int64_t* idx, float* dtable, int64_t n_idx, int dim,
+                                cudaStream_t stream) {
+    EW_LAUNCH(embedding_bwd_kernel, n_idx * dim, dout, idx, dtable, n_idx, dim);
+}
+// mode 0: assign, 1: +=, 2: atomicAdd
+HA2G_API int ha2g_copy_cols(const float* src, int src_ld, int src_off, int src_div, float* dst, int dst_ld, int dst_off,
+                            int dst_div, int64_t rows, int ncols, int mode, cudaStream_t stream) {
+    EW_LAUNCH(copy_cols_kernel, rows * ncols, src, src_ld, src_off, src_div, dst, dst_ld, dst_off, dst_div, rows, ncols,
+              mode);
+}
+HA2G_API int ha2g_gather_cols(const float* src, int src_ld, const int* idx, int n_idx, float* dst, int dst_ld,
+                              int64_t rows, cudaStream_t stream) {
+    EW_LAUNCH(gather_cols_kernel, rows * n_idx, src, src_ld, idx, n_idx, dst, dst_ld, rows);
+}
+// embedding_net.py:10-13
+HA2G_API int ha2g_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, int64_t n,
+                              cudaStream_t stream) {
+    EW_LAUNCH(reparam_fwd_kernel, n, mu, logvar, eps, z, n);
+}
+HA2G_API int ha2g_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar,
+                              int64_t n, cudaStream_t stream) {
+    EW_LAUNCH(reparam_bwd_kernel, n, dz, logvar, eps, dmu, dlogvar, n);
+}
+// tcn.py:19-24 weight_norm(Conv1d): g [O], v [O][I][Kw] -> wcat [O][Kw*I], norm [O]
+HA2G_API int ha2g_tcn_weight_fwd(const float* g, const float* v, float* wcat, float* norm, int O, int I, int Kw,
+                                 cudaStream_t stream) {
+    tcn_weight_fwd_kernel<<<O, 256, 0, stream>>>(g, v, wcat, norm, I, Kw);
+    HA2G_RETURN_LAST();
+}
+HA2G_API int ha2g_tcn_weight_bwd(const float* dwcat, const float* g, const float* v, const float* norm, float* dg,
+                                 float* dv, int O, int I, int Kw, cudaStream_t stream) {
+    tcn_weight_bwd_kernel<<<O, 256, 0, stream>>>(dwcat, g, v, norm, dg, dv, I, Kw);
+    HA2G_RETURN_LAST();
+}
+// causal dilated k=2 conv input staging (tcn.py:19-21 padding + Chomp1d)
+HA2G_API int ha2g_shift_concat_fwd(const float* x, float* out, int64_t B, int T, int C, int d, cudaStream_t stream) {
+    EW_LAUNCH(shift_concat_fwd_kernel, B * T * 2 * C, x, out, B, T, C, d);
+}
+HA2G_API int ha2g_shift_concat_bwd(const float* dout, float* dx, int64_t B, int T, int C, int d, cudaStream_t stream) {
+    EW_LAUNCH(shift_concat_bwd_kernel, B * T * C, dout, dx, B, T, C, d);
+}
+HA2G_API int ha2g_pre_seq_fwd(const float* target_k, const float* prev_out, int dp, const int* slot_src, float* pre,
+                              int64_t B, int T, int d, int n_pre, cudaStream_t stream) {
+    EW_LAUNCH(pre_seq_fwd_kernel, B * T * (d + 1), target_k, prev_out, dp, slot_src, pre, B, T, d, n_pre);
+}
+HA2G_API int ha2g_pre_seq_bwd(const float* dpre, int w, const int* src_slot, float* dprev, int64_t B, int T, int dp,
+                              int n_pre, cudaStream_t stream) {
+    EW_LAUNCH(pre_seq_bwd_kernel, B * T * dp, dpre, w, src_slot, dprev, B, T, dp, n_pre);
+}
+
+namespace {
+// x [B,T,C] -> out [B,To,Kw*C] with out[b,t,k*C+c] = x[b,t+k,c]   (valid Conv1d as a GEMM; To = T-Kw+1)
+__global__ void unfold1d_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t B, int T, int C, int Kw) {
+    const int To = T - Kw + 1, W = Kw * C;
+    const int64_t n = B * To * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int kc = (int)(i % W);
+        int64_t bt = i / W;
+        int t = (int)(bt % To);
+        int64_t b = bt / To;
+        int k = kc / C, c = kc % C;
+        out[i] = x[(b * T + t + k) * C + c];
+    }
+}
+// dx[b,t,c] = sum_k dout[b,t-k,k*C+c] over valid t-k in [0,To)
+__global__ void unfold1d_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int64_t B, int T, int C, int Kw) {
+    const int To = T - Kw + 1, W = Kw * C;
+    const int64_t n = B * T * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int64_t bt = i / C;
+        int t = (int)(bt % T);
+        int64_t b = bt / T;
+        float v = 0.f;
+        for (int k = 0; k < Kw; ++k) {
+            int to = t - k;
+            if (to >= 0 && to < To) v += dout[(b * To + to) * W + k * C + c];
+        }
+        dx[i] = v;
+    }
+}
+// inverse == 0: wp[o][k*I+i] = w[o][i][k];  inverse != 0: w[o][i][k] = wp[o][k*I+i]
+__global__ void pack_conv1d_w_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int Kw, int inverse) {
+    const int64_t n = (int64_t)O * I * Kw;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(e % Kw);
+        int i = (int)((e / Kw) % I);
+        int64_t o = e / ((int64_t)Kw * I);
+        int64_t packed = o * Kw * I + (int64_t)k * I + i;
+        if (inverse) dst[e] = src[packed]; else dst[packed] = src[e];
+    }
+}
+}  // namespace
+
+// Conv1d (no padding) input staging for the discriminator front-end (hierarchy_net.py:202-211)
+HA2G_API int ha2g_unfold1d_fwd(const float* x, float* out, int64_t B, int T, int C, int Kw, cudaStream_t stream) {
+    EW_LAUNCH(unfold1d_fwd_kernel, B * (T - Kw + 1) * Kw * C, x, out, B, T, C, Kw);
+}
+HA2G_API int ha2g_unfold1d_bwd(const float* dout, float* dx, int64_t B, int T, int C, int Kw, cudaStream_t stream) {
+    EW_LAUNCH(unfold1d_bwd_kernel, B * T * C, dout, dx, B, T, C, Kw);
+}
+// Conv1d weight [O][I][Kw] <-> GEMM layout [O][Kw*I]
+HA2G_API int ha2g_pack_conv1d_w(const float* src, float* dst, int O, int I, int Kw, int inverse, cudaStream_t stream) {
+    EW_LAUNCH(pack_conv1d_w_kernel, (int64_t)O * I * Kw, src, dst, O, I, Kw, inverse);
+}

@@ -1,0 +1,422 @@
+// Loss kernels of the HA2G step (K15-K18 of SURVEY.md).  Every forward kernel also emits the
+// un-scaled gradient of its scalar wrt its input, so backward is one multiply by the upstream
+// device scalar (no host sync anywhere).
+//   Huber                 train_hierarchy_expressive.py:312-318
+//   GAN log losses        :224, :322
+//   KLD                   :410
+//   diversity regulariser :396-406
+//   physical (bone angle) :426-449 (expressive, 42 bones + 2 palm normals) / train_hierarchy.py:242-262
+//   contrastive           SoftmaxContrastiveLoss, train_hierarchy.py:54-68 / ..._expressive.py:108-121
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+// loss += beta * mean(smooth_l1((o-t)/beta));  grad[i] = clamp((o-t)/beta, -1, 1) / n
+__global__ void huber_kernel(const float* __restrict__ o, const float* __restrict__ t, float* __restrict__ grad, int64_t n,
+                             float beta, float* __restrict__ loss) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    const float invb = 1.f / beta, invn = 1.f / (float)n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x = o[i] * invb - t[i] * invb;  // matches (o/beta - t/beta) of the reference
+        float ax = fabsf(x);
+        acc += ax < 1.f ? 0.5f * x * x : ax - 0.5f;
+        if (grad != nullptr) grad[i] = fminf(fmaxf(x, -1.f), 1.f) * invn;
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, acc * beta * invn);
+}
+
+// mode 0: loss += -mean(log(x + 1e-8)),     grad = -1/(n (x+1e-8))
+// mode 1: loss += -mean(log(1 - x + 1e-8)), grad = +1/(n (1-x+1e-8))
+__global__ void log_loss_kernel(const float* __restrict__ x, float* __restrict__ grad, int64_t n, int mode,
+                                float* __restrict__ loss) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    const float invn = 1.f / (float)n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = x[i];
+        if (mode == 0) {
+            float a = v + 1e-8f;
+            acc -= logf(a);
+            if (grad != nullptr) grad[i] = -invn / a;
+        } else {
+            float a = 1.f - v + 1e-8f;
+            acc -= logf(a);
+            if (grad != nullptr) grad[i] = invn / a;
+        }
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, acc * invn);
+}
+
+// kld = -0.5 * mean(1 + lv - mu^2 - exp(lv));  dmu = mu/n;  dlv = -0.5 (1 - exp(lv))/n
+__global__ void kld_kernel(const float* __restrict__ mu, const float* __restrict__ lv, float* __restrict__ dmu,
+                           float* __restrict__ dlv, int64_t n, float* __restrict__ loss) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    const float invn = 1.f / (float)n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float m = mu[i], l = lv[i], e = expf(l);
+        acc += 1.f + l - m * m - e;
+        dmu[i] = m * invn;
+        dlv[i] = -0.5f * (1.f - e) * invn;
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, -0.5f * acc * invn);
+}
+
+// one CTA per sample b:  pose_l1 = sum_{t,d} beta*smooth_l1((o-r)/beta);  z_l1 = mean_j |z - zr|
+// div_b = max(-pose_l1/(z_l1+1e-5), -1000);  loss += div_b / B;  grad[b,:] = d div_b/d o / B
+__global__ void div_reg_kernel(const float* __restrict__ o, const float* __restrict__ r, const float* __restrict__ z,
+                               const float* __restrict__ zr, float* __restrict__ grad, int B, int TD, int Z, float beta,
+                               float* __restrict__ loss) {
+    __shared__ float sh[33];
+    const int b = blockIdx.x;
+    const float invb = 1.f / beta;
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < TD; e += blockDim.x) {
+        float x = o[(size_t)b * TD + e] * invb - r[(size_t)b * TD + e] * invb;
+        float ax = fabsf(x);
+        acc += (ax < 1.f ? 0.5f * x * x : ax - 0.5f) * beta;
+    }
+    const float pose = block_sum(acc, sh);
+    float za = 0.f;
+    for (int e = threadIdx.x; e < Z; e += blockDim.x) za += fabsf(z[(size_t)b * Z + e] - zr[(size_t)b * Z + e]);
+    const float zl1 = block_sum(za, sh) / (float)Z;
+    const float den = zl1 + 1.0e-5f;
+    const float val = -pose / den;
+    const bool live = val >= -1000.f;
+    if (threadIdx.x == 0) atomicAdd(loss, fmaxf(val, -1000.f) / (float)B);
+    const float coef = live ? -1.f / (den * (float)B) : 0.f;
+    for (int e = threadIdx.x; e < TD; e += blockDim.x) {
+        float x = o[(size_t)b * TD + e] * invb - r[(size_t)b * TD + e] * invb;
+        grad[(size_t)b * TD + e] = coef * fminf(fmaxf(x, -1.f), 1.f);
+    }
+}
+
+__global__ void scale_by_scalar_kernel(const float* __restrict__ x, const float* __restrict__ s, float alpha,
+                                       float* __restrict__ out, int64_t n, int accumulate) {
+    const float f = alpha * (s != nullptr ? *s : 1.f);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = accumulate ? out[i] + f * x[i] : f * x[i];
+}
+
+// ---- physical loss: one warp per (b,t) row -------------------------------------------------------------
+constexpr int PHY_MAXV = 44;
+constexpr int PHY_MAXP = 48;
+__constant__ int c_phy_pairs[2][PHY_MAXP][2];
+__constant__ float c_phy_avg[2][PHY_MAXP];
+__constant__ float c_phy_var[2][PHY_MAXP];
+__constant__ float c_phy_mean[2][3 * 42];
+
+// variant 0: gesture (9 bones, 4 pairs, no palms), 1: expressive (42 bones + 2 palms, 41 pairs)
+__global__ void physical_kernel(const float* __restrict__ out, float* __restrict__ grad, int64_t rows, int variant,
+                                int nb, int npairs, float* __restrict__ loss) {
+    constexpr int WPB = 4;
+    __shared__ float raw[WPB][PHY_MAXV * 3];
+    __shared__ float unit[WPB][PHY_MAXV * 3];
+    __shared__ float nrm[WPB][PHY_MAXV];
+    __shared__ float dun[WPB][PHY_MAXV * 3];
+    __shared__ float wl[WPB];
+    const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int64_t row = (int64_t)blockIdx.x * WPB + w;
+    const bool active = row < rows;
+    const int D = nb * 3;
+    const int nv = variant == 1 ? nb + 2 : nb;
+    float lsum = 0.f;
+    if (active) {
+        for (int e = lane; e < D; e += 32) raw[w][e] = out[row * D + e] + c_phy_mean[variant][e];
+        for (int e = lane; e < nv * 3; e += 32) dun[w][e] = 0.f;
+    }
+    __syncwarp();
+    if (active && variant == 1 && lane < 2) {
+        // palm normals: cross(bone 11, bone 17) -> vec 42; cross(bone 28, bone 34) -> vec 43
+        const int a = lane == 0 ? 11 : 28, b = lane == 0 ? 17 : 34;
+        const float ax = raw[w][a * 3], ay = raw[w][a * 3 + 1], az = raw[w][a * 3 + 2];
+        const float bx = raw[w][b * 3], by = raw[w][b * 3 + 1], bz = raw[w][b * 3 + 2];
+        raw[w][(nb + lane) * 3 + 0] = ay * bz - az * by;
+        raw[w][(nb + lane) * 3 + 1] = az * bx - ax * bz;
+        raw[w][(nb + lane) * 3 + 2] = ax * by - ay * bx;
+    }
+    __syncwarp();
+    if (active) {
+        for (int v = lane; v < nv; v += 32) {
+            float x = raw[w][v * 3], y = raw[w][v * 3 + 1], z = raw[w][v * 3 + 2];
+            float n = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+            nrm[w][v] = n;
+            unit[w][v * 3] = x / n; unit[w][v * 3 + 1] = y / n; unit[w][v * 3 + 2] = z / n;
+        }
+    }
+    __syncwarp();
+    const float lo = (float)(-1.0 + 1e-7), hi = (float)(1.0 - 1e-7);
+    const float inv_rows = 1.f / (float)rows;
+    if (active) {
+        for (int p = lane; p < npairs; p += 32) {
+            const int i0 = c_phy_pairs[variant][p][0], i1 = c_phy_pairs[variant][p][1];
+            const float* u0 = &unit[w][i0 * 3];
+            const float* u1 = &unit[w][i1 * 3];
+            float ip = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
+            const bool inside = ip >= lo && ip <= hi;
+            ip = fminf(fmaxf(ip, lo), hi);
+            const float ang = acosf(ip) / CUDART_PI_F;
+            const float dlt = ang - c_phy_avg[variant][p];
+            const float iv = 1.f / (2.f * c_phy_var[variant][p]);
+            lsum += dlt * dlt * iv;
+            if (grad != nullptr && inside) {
+                // d/d ip: 2*dlt*iv * (1/pi) * (-1/sqrt(1-ip^2)) / rows
+                const float gip = 2.f * dlt * iv * (-1.f / (CUDART_PI_F * sqrtf(1.f - ip * ip))) * inv_rows;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    atomicAdd(&dun[w][i0 * 3 + c], gip * u1[c]);
+                    atomicAdd(&dun[w][i1 * 3 + c], gip * u0[c]);
+                }
+            }
+        }
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) wl[w] = active ? lsum : 0.f;
+    __syncwarp();
+    if (grad != nullptr && active) {
+        // normalize backward: draw = (du - (du . u) u) / max(|raw|, eps)   (in place in dun)
+        for (int v = lane; v < nv; v += 32) {
+            float dx = dun[w][v * 3], dy = dun[w][v * 3 + 1], dz = dun[w][v * 3 + 2];
+            float ux = unit[w][v * 3], uy = unit[w][v * 3 + 1], uz = unit[w][v * 3 + 2];
+            float dot = dx * ux + dy * uy + dz * uz;
+            float inv = 1.f / nrm[w][v];
+            dun[w][v * 3] = (dx - dot * ux) * inv; dun[w][v * 3 + 1] = (dy - dot * uy) * inv; dun[w][v * 3 + 2] = (dz - dot * uz) * inv;
+        }
+        __syncwarp();
+        if (variant == 1 && lane < 2) {
+            // c = a x b:  da += b x dc,  db += dc x a
+            const int a = lane == 0 ? 11 : 28, b = lane == 0 ? 17 : 34, cidx = nb + lane;
+            const float ax = raw[w][a * 3], ay = raw[w][a * 3 + 1], az = raw[w][a * 3 + 2];
+            const float bx = raw[w][b * 3], by = raw[w][b * 3 + 1], bz = raw[w][b * 3 + 2];
+            const float cx = dun[w][cidx * 3], cy = dun[w][cidx * 3 + 1], cz = dun[w][cidx * 3 + 2];
+            atomicAdd(&dun[w][a * 3 + 0], by * cz - bz * cy);
+            atomicAdd(&dun[w][a * 3 + 1], bz * cx - bx * cz);
+            atomicAdd(&dun[w][a * 3 + 2], bx * cy - by * cx);
+            atomicAdd(&dun[w][b * 3 + 0], cy * az - cz * ay);
+            atomicAdd(&dun[w][b * 3 + 1], cz * ax - cx * az);
+            atomicAdd(&dun[w][b * 3 + 2], cx * ay - cy * ax);
+        }
+        __syncwarp();
+        for (int e = lane; e < D; e += 32) grad[row * D + e] = dun[w][e];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < WPB; ++i) t += wl[i];
+        atomicAdd(loss, t * inv_rows);
+    }
+}
+
+// ---- contrastive --------------------------------------------------------------------------------------
+constexpr int CC = 32;      // feature width (nOut of both encoders)
+constexpr int CT = 128;     // rows per CTA / tile
+
+// xn = x / max(|x|, 1e-12), norms saved.   one warp per row, lane = channel
+__global__ void l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ nrm, int64_t N) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= N) return;
+    float v = x[row * CC + lane];
+    float s = warp_sum(v * v);
+    float n = fmaxf(sqrtf(s), 1e-12f);
+    xn[row * CC + lane] = v / n;
+    if (lane == 0) nrm[row] = n;
+}
+// dx = (dn - (dn . n) n) / norm
+__global__ void l2norm_rows_bwd_kernel(const float* __restrict__ dn, const float* __restrict__ xn,
+                                       const float* __restrict__ nrm, float* __restrict__ dx, int64_t N) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= N) return;
+    float g = dn[row * CC + lane], n = xn[row * CC + lane];
+    float dot = warp_sum(g * n);
+    dx[row * CC + lane] = (g - dot * n) / nrm[row];
+}
+
+__device__ __forceinline__ float contrastive_logit(float d, int variant) {
+    return variant == 0 ? fmaxf(1.0f / (d + 1e-8f), 1e-8f) : 1.0f / d;
+}
+
+// MODE 0: forward partial (max, sumexp) of row i over the column split -> part[i][split][2]; diag logit -> diag[i]
+// MODE 1: gradient wrt the OWNED rows (rows of `own`), other side streamed.  own_is_a: owned rows are a (loss rows i)
+//         da_i += sum_j c_ij (a_i - b_j)      c_ij = gs * (p_ij - delta_ij) * dl/dD / D,   p_ij = exp(l_ij - lse_i)
+//         (own_is_a == 0): db_j += sum_i c_ij (b_j - a_i)
+template <int MODE>
+__global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __restrict__ own, const float* __restrict__ oth,
+                                                              const float* __restrict__ lse, float* __restrict__ part,
+                                                              float* __restrict__ diag, float* __restrict__ dgrad,
+                                                              const float* __restrict__ gscale, int N, int variant,
+                                                              int own_is_a, int cols_per_split) {
+    __shared__ float tile[CT][CC + 1];
+    __shared__ float tlse[CT];
+    const int i = blockIdx.x * CT + threadIdx.x;
+    const bool valid = i < N;
+    float me[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) me[c] = valid ? own[(size_t)i * CC + c] : 0.f;
+    const int j_beg = blockIdx.y * cols_per_split, j_end = min(N, j_beg + cols_per_split);
+    float m = -CUDART_INF_F, s = 0.f;
+    float acc[CC];
+    float my_lse = 0.f, gs = 0.f;
+    if (MODE == 1) {
+#pragma unroll
+        for (int c = 0; c < CC; ++c) acc[c] = 0.f;
+        gs = (gscale != nullptr ? *gscale : 1.f) / (float)N;
+        if (own_is_a && valid) my_lse = lse[i];
+    }
+    for (int j0 = j_beg; j0 < j_end; j0 += CT) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < CT * CC; e += CT) {
+            int r = e / CC, c = e % CC;
+            int j = j0 + r;
+            tile[r][c] = j < j_end ? oth[(size_t)j * CC + c] : 0.f;
+        }
+        if (MODE == 1 && !own_is_a) {
+            int j = j0 + threadIdx.x;
+            tlse[threadIdx.x] = j < j_end ? lse[j] : 0.f;
+        }
+        __syncthreads();
+        if (!valid) continue;
+        const int cnt = min(CT, j_end - j0);
+        for (int r = 0; r < cnt; ++r) {
+            float d2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CC; ++c) { float df = me[c] - tile[r][c]; d2 = fmaf(df, df, d2); }
+            const float d = sqrtf(d2);
+            const float l = contrastive_logit(d, variant);
+            const int j = j0 + r;
+            if (MODE == 0) {
+                if (j == i) diag[i] = l;
+                if (l > m) { s = s * expf(m - l) + 1.f; m = l; }
+                else s += expf(l - m);
+            } else {
+                const float row_lse = own_is_a ? my_lse : tlse[r];
+                float p = expf(l - row_lse);
+                if (j == i) p -= 1.f;
+                float dld;
+                if (variant == 0) { float t = d + 1e-8f; dld = -1.f / (t * t); }
+                else dld = -1.f / (d * d);
+                float cf = d > 0.f ? gs * p * dld / d : 0.f;
+#pragma unroll
+                for (int c = 0; c < CC; ++c) acc[c] = fmaf(cf, me[c] - tile[r][c], acc[c]);
+            }
+        }
+    }
+    if (!valid) return;
+    if (MODE == 0) {
+        part[((size_t)i * gridDim.y + blockIdx.y) * 2 + 0] = m;
+        part[((size_t)i * gridDim.y + blockIdx.y) * 2 + 1] = s;
+    } else {
+#pragma unroll
+        for (int c = 0; c < CC; ++c) atomicAdd(dgrad + (size_t)i * CC + c, acc[c]);
+    }
+}
+
+// lse_i from the split partials; loss += mean_i (lse_i - l_ii)
+__global__ void contrastive_finalize_kernel(const float* __restrict__ part, const float* __restrict__ diag, int N, int S,
+                                            float* __restrict__ lse, float* __restrict__ loss) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        float m = -CUDART_INF_F;
+        for (int k = 0; k < S; ++k) m = fmaxf(m, part[((size_t)i * S + k) * 2]);
+        float s = 0.f;
+        for (int k = 0; k < S; ++k) s += part[((size_t)i * S + k) * 2 + 1] * expf(part[((size_t)i * S + k) * 2] - m);
+        float l = m + logf(s);
+        lse[i] = l;
+        acc += l - diag[i];
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, acc / (float)N);
+}
+
+}  // namespace
+
+// loss (device scalar, ACCUMULATED) += beta*mean(smooth_l1(o/beta, t/beta));  grad (nullable) = d/d o, unscaled
+HA2G_API int ha2g_huber(const float* o, const float* t, float* grad, int64_t n, float beta, float* loss,
+                        cudaStream_t stream) {
+    huber_kernel<<<ha2g_ew_grid(n), 256, 0, stream>>>(o, t, grad, n, beta, loss);
+    HA2G_RETURN_LAST();
+}
+// mode 0: -mean(log(x+1e-8)); mode 1: -mean(log(1-x+1e-8));  loss ACCUMULATED
+HA2G_API int ha2g_log_loss(const float* x, float* grad, int64_t n, int mode, float* loss, cudaStream_t stream) {
+    log_loss_kernel<<<ha2g_ew_grid(n), 256, 0, stream>>>(x, grad, n, mode, loss);
+    HA2G_RETURN_LAST();
+}
+HA2G_API int ha2g_kld(const float* mu, const float* logvar, float* dmu, float* dlogvar, int64_t n, float* loss,
+                      cudaStream_t stream) {
+    kld_kernel<<<ha2g_ew_grid(n), 256, 0, stream>>>(mu, logvar, dmu, dlogvar, n, loss);
+    HA2G_RETURN_LAST();
+}
+// o, r: [B,TD];  z, zr: [B,Z];  grad [B,TD] = d loss / d o (unscaled);  loss ACCUMULATED
+HA2G_API int ha2g_div_reg(const float* o, const float* r, const float* z, const float* zr, float* grad, int B, int TD,
+                          int Z, float beta, float* loss, cudaStream_t stream) {
+    div_reg_kernel<<<B, 256, 0, stream>>>(o, r, z, zr, grad, B, TD, Z, beta, loss);
+    HA2G_RETURN_LAST();
+}
+// out = alpha * (*s) * x  (s nullable => 1);  accumulate != 0: out += ...
+HA2G_API int ha2g_scale_by_scalar(const float* x, const float* s, float alpha, float* out, int64_t n, int accumulate,
+                                  cudaStream_t stream) {
+    if (n <= 0) return 0;
+    scale_by_scalar_kernel<<<ha2g_ew_grid(n), 256, 0, stream>>>(x, s, alpha, out, n, accumulate);
+    HA2G_RETURN_LAST();
+}
+// Upload the physical-loss tables (host pointers): pairs [npairs][2], avg/var [npairs], mean_dir_vec [3*nb].
+HA2G_API int ha2g_physical_set_tables(int variant, const int* pairs, const float* avg, const float* var, int npairs,
+                                      const float* mean_dir_vec, int nb) {
+    if (variant < 0 || variant > 1 || npairs > PHY_MAXP || nb > 42) return (int)cudaErrorInvalidValue;
+    cudaError_t e;
+    e = cudaMemcpyToSymbol(c_phy_pairs, pairs, sizeof(int) * 2 * npairs, sizeof(int) * 2 * PHY_MAXP * variant);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(c_phy_avg, avg, sizeof(float) * npairs, sizeof(float) * PHY_MAXP * variant);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(c_phy_var, var, sizeof(float) * npairs, sizeof(float) * PHY_MAXP * variant);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(c_phy_mean, mean_dir_vec, sizeof(float) * 3 * nb, sizeof(float) * 3 * 42 * variant);
+    return (int)e;
+}
+// out [rows, 3*nb]; loss ACCUMULATED += sum_p mean_rows((angle_p - avg_p)^2 / (2 var_p)); grad nullable, unscaled
+HA2G_API int ha2g_physical(const float* out, float* grad, int64_t rows, int variant, int nb, int npairs, float* loss,
+                           cudaStream_t stream) {
+    physical_kernel<<<ha2g_div_up(rows, 4), 128, 0, stream>>>(out, grad, rows, variant, nb, npairs, loss);
+    HA2G_RETURN_LAST();
+}
+// Contrastive forward.  a, b: [N,32].  Outputs: an, bn [N,32], na, nb [N] (normalised rows + norms), lse [N],
+// loss ACCUMULATED.  scratch: part [N * ceil(N/128) * 2] floats (upper bound), diag [N].
+static int contrastive_splits(int N) {
+    int rows_ctas = (N + CT - 1) / CT;
+    int s = (148 * 2 + rows_ctas - 1) / rows_ctas;
+    int max_s = (N + CT - 1) / CT;
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    return s;
+}
+HA2G_API int ha2g_contrastive_fwd(const float* a, const float* b, float* an, float* bn, float* na, float* nb, float* lse,
+                                  float* part, float* diag, int N, int variant, float* loss, cudaStream_t stream) {
+    const int S = contrastive_splits(N);
+    const int cols = ((N + S - 1) / S + CT - 1) / CT * CT;
+    l2norm_rows_kernel<<<ha2g_div_up(N, 8), 256, 0, stream>>>(a, an, na, N);
+    l2norm_rows_kernel<<<ha2g_div_up(N, 8), 256, 0, stream>>>(b, bn, nb, N);
+    dim3 grid(ha2g_div_up(N, CT), ha2g_div_up(N, cols));
+    contrastive_pair_kernel<0><<<grid, CT, 0, stream>>>(an, bn, nullptr, part, diag, nullptr, nullptr, N, variant, 1, cols);
+    contrastive_finalize_kernel<<<ha2g_div_up(N, 256), 256, 0, stream>>>(part, diag, N, grid.y, lse, loss);
+    HA2G_RETURN_LAST();
+}
+// Contrastive backward: da, db [N,32] = gscale * d loss/d a, d loss/d b.  dan, dbn: zero-initialised scratch [N,32].
+HA2G_API int ha2g_contrastive_bwd(const float* an, const float* bn, const float* na, const float* nb, const float* lse,
+                                  const float* gscale, float* dan, float* dbn, float* da, float* db, int N, int variant,
+                                  cudaStream_t stream) {
+    const int S = contrastive_splits(N);
+    const int cols = ((N + S - 1) / S + CT - 1) / CT * CT;
+    dim3 grid(ha2g_div_up(N, CT), ha2g_div_up(N, cols));
+    contrastive_pair_kernel<1><<<grid, CT, 0, stream>>>(an, bn, lse, nullptr, nullptr, dan, gscale, N, variant, 1, cols);
+    contrastive_pair_kernel<1><<<grid, CT, 0, stream>>>(bn, an, lse, nullptr, nullptr, dbn, gscale, N, variant, 0, cols);
+    l2norm_rows_bwd_kernel<<<ha2g_div_up(N, 8), 256, 0, stream>>>(dan, an, na, da, N);
+    l2norm_rows_bwd_kernel<<<ha2g_div_up(N, 8), 256, 0, stream>>>(dbn, bn, nb, db, N);
+    HA2G_RETURN_LAST();
+}

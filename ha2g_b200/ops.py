@@ -1,0 +1,573 @@
+"""Differentiable ops of the HA2G step, each backed by hand-written sm_100a kernels (csrc/*.cu).
+
+PyTorch is used here only as the device-memory allocator, stream owner and autograd tape; every
+arithmetic operation is a launch through the C ABI (ha2g_b200._lib.lib).  There is no fallback:
+CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from ._lib import lib
+from . import rng as _rng
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_ELU, ACT_SIGMOID, ACT_TANH = range(6)
+
+LAUNCHES = [0]  # number of C-ABI launcher calls (bench.py reports it as gpu_launches)
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("ha2g_b200 ops need CUDA tensors (no CPU fallback path exists)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"expected float32, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("expected a contiguous tensor")
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _call(name: str, *args):
+    LAUNCHES[0] += 1
+    getattr(lib, name)(*args)
+
+
+# ------------------------------------------------------------------------------------------------
+# raw helpers
+# ------------------------------------------------------------------------------------------------
+def gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, tA=0, tB=0, act=0, acc=0, split=1):
+    _call("ha2g_gemm_f32", _p(A), _p(B), _p(C), _p(bias), M, N, K, lda, ldb, ldc, tA, tB, act, acc, split, _st())
+
+
+def col_sum_into(x2d: torch.Tensor, out: torch.Tensor):
+    rows, cols = x2d.shape
+    _call("ha2g_col_sum", _p(x2d), rows, cols, x2d.stride(0), _p(out), _st())
+
+
+def _split_for(rows: int, m: int, n: int) -> int:
+    """split-K factor for weight-gradient GEMMs: enough CTAs to cover the 148 SMs."""
+    tiles = ((m + 127) // 128) * ((n + 63) // 64)
+    s = max(1, min(32, (148 + tiles - 1) // tiles))
+    while s > 1 and rows // s < 64:
+        s //= 2
+    return max(1, s)
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear (+ fused activation)
+# ------------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        x2 = _c(x.reshape(-1, x.shape[-1]))
+        _chk(x2, w, b)
+        R, K = x2.shape
+        N = w.shape[0]
+        y = torch.empty((R, N), device=x.device, dtype=torch.float32)
+        gemm(x2, w, y, b, R, N, K, K, K, N, 0, 1, act, 0, 1)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.xshape = x.shape
+        ctx.save_for_backward(x2, w, y if act else None)
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        R, K = x2.shape
+        N = w.shape[0]
+        g = _c(dy.reshape(R, N))
+        if ctx.act:
+            g2 = torch.empty_like(g)
+            _call("ha2g_act_bwd", _p(g), _p(y), _p(g2), g.numel(), ctx.act, _st())
+            g = g2
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((R, K), device=g.device, dtype=torch.float32)
+            gemm(g, w, dx, None, R, K, N, N, K, K, 0, 0, 0, 0, 1)
+            dx = dx.reshape(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w)
+            gemm(g, x2, dw, None, N, K, R, N, K, K, 1, 0, 0, 1, _split_for(R, N, K))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros((N,), device=g.device, dtype=torch.float32)
+            col_sum_into(g, db)
+        return dx, dw, db, None
+
+
+def linear(x, w, b=None, act=ACT_NONE):
+    return _LinearFn.apply(x, w, b, act)
+
+
+# ------------------------------------------------------------------------------------------------
+# element-wise
+# ------------------------------------------------------------------------------------------------
+class _ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        x = _c(x)
+        _chk(x)
+        y = torch.empty_like(x)
+        _call("ha2g_act_fwd", _p(x), _p(y), x.numel(), act, _st())
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        _call("ha2g_act_bwd", _p(dy), _p(y), _p(dx), dy.numel(), ctx.act, _st())
+        return dx, None
+
+
+def act(x, code):
+    return _ActFn.apply(x, code)
+
+
+class _AddActFn(torch.autograd.Function):
+    """y = act(a + b)"""
+
+    @staticmethod
+    def forward(ctx, a, b, act):
+        a, b = _c(a), _c(b)
+        _chk(a, b)
+        y = torch.empty_like(a)
+        _call("ha2g_add_act_fwd", _p(a), _p(b), _p(y), a.numel(), act, _st())
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        if ctx.act:
+            dx = torch.empty_like(dy)
+            _call("ha2g_act_bwd", _p(dy), _p(y), _p(dx), dy.numel(), ctx.act, _st())
+        else:
+            dx = dy
+        return dx, dx, None
+
+
+def add_act(a, b, code=ACT_NONE):
+    return _AddActFn.apply(a, b, code)
+
+
+class _MulMaskFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, scale):
+        x = _c(x)
+        _chk(x, mask)
+        y = torch.empty_like(x)
+        _call("ha2g_mul_mask", _p(x), _p(mask), scale, _p(y), x.numel(), _st())
+        ctx.scale = scale
+        ctx.save_for_backward(mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        _call("ha2g_mul_mask", _p(dy), _p(mask), ctx.scale, _p(dx), dy.numel(), _st())
+        return dx, None, None
+
+
+def dropout(x, p: float, training: bool):
+    """nn.Dropout semantics; the keep-mask comes from ha2g_b200.rng (injectable for parity tests)."""
+    if not training or p <= 0.0 or not _rng.dropout_enabled():
+        return x
+    mask = _rng.dropout_mask(x.shape, p, x.device)
+    return _MulMaskFn.apply(x, mask, 1.0 / (1.0 - p))
+
+
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, idx):
+        _chk(table)
+        idx = _c(idx)
+        if idx.dtype != torch.int64 or not idx.is_cuda:
+            raise RuntimeError("embedding indices must be CUDA int64")
+        dim = table.shape[1]
+        out = torch.empty((*idx.shape, dim), device=table.device, dtype=torch.float32)
+        _call("ha2g_embedding_fwd", _p(table), _p(idx), _p(out), idx.numel(), dim, _st())
+        ctx.save_for_backward(idx)
+        ctx.tshape = table.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dout = _c(dout)
+        dt = torch.zeros(ctx.tshape, device=dout.device, dtype=torch.float32)
+        _call("ha2g_embedding_bwd", _p(dout), _p(idx), _p(dt), idx.numel(), ctx.tshape[1], _st())
+        return dt, None
+
+
+def embedding(table, idx):
+    return _EmbeddingFn.apply(table, idx)
+
+
+class _ReparamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        mu, logvar, eps = _c(mu), _c(logvar), _c(eps)
+        _chk(mu, logvar, eps)
+        z = torch.empty_like(mu)
+        _call("ha2g_reparam_fwd", _p(mu), _p(logvar), _p(eps), _p(z), mu.numel(), _st())
+        ctx.save_for_backward(logvar, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        logvar, eps = ctx.saved_tensors
+        dz = _c(dz)
+        dmu = torch.empty_like(dz)
+        dlv = torch.empty_like(dz)
+        _call("ha2g_reparam_bwd", _p(dz), _p(logvar), _p(eps), _p(dmu), _p(dlv), dz.numel(), _st())
+        return dmu, dlv, None
+
+
+def reparameterize(mu, logvar):
+    """embedding_net.py:10-13; the noise draw comes from ha2g_b200.rng."""
+    eps = _rng.randn(mu.shape, mu.device)
+    return _ReparamFn.apply(mu, logvar, eps)
+
+
+class _ConcatSeqFn(torch.autograd.Function):
+    """cat((pre_seq, audio, text, z.repeat over T), dim=2)   (hierarchy_net.py:129,140-142)."""
+
+    @staticmethod
+    def forward(ctx, pre, audio, text, z):
+        pre, audio, text, z = _c(pre), _c(audio), _c(text), _c(z)
+        _chk(pre, audio, text, z)
+        B, T, dp = pre.shape
+        widths = [dp, audio.shape[2], text.shape[2], z.shape[1]]
+        I = sum(widths)
+        x = torch.empty((B, T, I), device=pre.device, dtype=torch.float32)
+        off = 0
+        for src, w, div in ((pre, widths[0], 1), (audio, widths[1], 1), (text, widths[2], 1), (z, widths[3], T)):
+            _call("ha2g_copy_cols", _p(src), w, 0, div, _p(x), I, off, 1, B * T, w, 0, _st())
+            off += w
+        ctx.widths, ctx.BT = widths, (B, T)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        dx = _c(dx)
+        B, T = ctx.BT
+        I = dx.shape[2]
+        outs, off = [], 0
+        for i, w in enumerate(ctx.widths):
+            if not ctx.needs_input_grad[i]:
+                outs.append(None)
+            elif i < 3:
+                g = torch.empty((B, T, w), device=dx.device, dtype=torch.float32)
+                _call("ha2g_copy_cols", _p(dx), I, off, 1, _p(g), w, 0, 1, B * T, w, 0, _st())
+                outs.append(g)
+            else:
+                g = torch.zeros((B, w), device=dx.device, dtype=torch.float32)
+                _call("ha2g_copy_cols", _p(dx), I, off, 1, _p(g), w, 0, T, B * T, w, 2, _st())
+                outs.append(g)
+            off += w
+        return tuple(outs)
+
+
+def concat_seq(pre, audio, text, z):
+    return _ConcatSeqFn.apply(pre, audio, text, z)
+
+
+# ------------------------------------------------------------------------------------------------
+# bidirectional multi-layer GRU
+# ------------------------------------------------------------------------------------------------
+class _BiGRUFn(torch.autograd.Function):
+    """nn.GRU(batch_first, bidirectional, num_layers=L, dropout=p) with h0 = 0.
+
+    weights: per layer [w_ih, w_hh, b_ih, b_hh, w_ih_rev, w_hh_rev, b_ih_rev, b_hh_rev]
+    (nn.GRU._flat_weights order).  sum_dirs: return y[..., :H] + y[..., H:]  (hierarchy_net.py:145).
+    """
+
+    @staticmethod
+    def forward(ctx, x, H, L, p, training, sum_dirs, *weights):
+        x = _c(x)
+        _chk(x, *weights)
+        M, T, _ = x.shape
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights))
+        saved: List[torch.Tensor] = []
+        masks = []
+        cur = x
+        for l in range(L):
+            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = weights[8 * l:8 * l + 8]
+            I = cur.shape[2]
+            gi = torch.empty((M, T, 6 * H), device=x.device, dtype=torch.float32)
+            y = torch.empty((M, T, 2 * H), device=x.device, dtype=torch.float32)
+            gates = torch.empty((M, T, 8 * H), device=x.device, dtype=torch.float32) if need_grad else None
+            _call("ha2g_gru_layer_fwd", _p(cur), I, _p(w_ih), _p(w_ih_r), _p(b_ih), _p(b_ih_r), _p(w_hh), _p(w_hh_r),
+                  _p(b_hh), _p(b_hh_r), _p(gi), _p(y), _p(gates), M, T, H, _st())
+            if need_grad:
+                saved += [cur, y, gates]
+            nxt = y
+            mask = None
+            if l < L - 1 and training and p > 0.0 and _rng.dropout_enabled():
+                mask = _rng.dropout_mask(y.shape, p, y.device)
+                nxt = torch.empty_like(y)
+                _call("ha2g_mul_mask", _p(y), _p(mask), 1.0 / (1.0 - p), _p(nxt), y.numel(), _st())
+            masks.append(mask)
+            cur = nxt
+        if sum_dirs:
+            out = torch.empty((M, T, H), device=x.device, dtype=torch.float32)
+            _call("ha2g_copy_cols", _p(cur), 2 * H, 0, 1, _p(out), H, 0, 1, M * T, H, 0, _st())
+            _call("ha2g_copy_cols", _p(cur), 2 * H, H, 1, _p(out), H, 0, 1, M * T, H, 1, _st())
+        else:
+            out = cur
+        ctx.cfg = (H, L, p, sum_dirs, M, T)
+        ctx.masks = masks
+        ctx.nw = len(weights)
+        ctx.save_for_backward(*saved, *weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        H, L, p, sum_dirs, M, T = ctx.cfg
+        st = ctx.saved_tensors
+        weights = st[len(st) - ctx.nw:]
+        saved = st[:len(st) - ctx.nw]
+        dev = dout.device
+        dy = _c(dout)
+        dy_ld, dy_ds = (H, 0) if sum_dirs else (2 * H, H)
+        grads: List[Optional[torch.Tensor]] = [None] * ctx.nw
+        dgi = torch.empty((M, T, 6 * H), device=dev, dtype=torch.float32)
+        dgh = torch.empty((M, T, 6 * H), device=dev, dtype=torch.float32)
+        dh = torch.empty((M, 2 * H), device=dev, dtype=torch.float32)
+        dx = None
+        for l in range(L - 1, -1, -1):
+            xin, y, gates = saved[3 * l:3 * l + 3]
+            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = weights[8 * l:8 * l + 8]
+            I = xin.shape[2]
+            g = [torch.zeros_like(w) for w in weights[8 * l:8 * l + 8]]
+            need_dx = l > 0 or ctx.needs_input_grad[0]
+            dx = torch.empty((M, T, I), device=dev, dtype=torch.float32) if need_dx else None
+            _call("ha2g_gru_layer_bwd", _p(dy), dy_ld, dy_ds, _p(xin), I, _p(y), _p(gates), _p(w_ih), _p(w_ih_r),
+                  _p(w_hh), _p(w_hh_r), _p(dgi), _p(dgh), _p(dh), _p(dx), _p(g[0]), _p(g[4]), _p(g[1]), _p(g[5]),
+                  _p(g[2]), _p(g[6]), _p(g[3]), _p(g[7]), M, T, H, _st())
+            grads[8 * l:8 * l + 8] = g
+            if l > 0:
+                mask = ctx.masks[l - 1]
+                if mask is not None:
+                    dy = torch.empty_like(dx)
+                    _call("ha2g_mul_mask", _p(dx), _p(mask), 1.0 / (1.0 - p), _p(dy), dx.numel(), _st())
+                else:
+                    dy = dx
+                dy_ld, dy_ds = 2 * H, H
+        return (dx, None, None, None, None, None, *grads)
+
+
+def bigru(x, weights: Sequence[torch.Tensor], H: int, L: int, p: float, training: bool, sum_dirs: bool = True):
+    return _BiGRUFn.apply(x, H, L, p, training, sum_dirs, *weights)
+
+
+# ------------------------------------------------------------------------------------------------
+# TCN pieces
+# ------------------------------------------------------------------------------------------------
+class _TcnWeightFn(torch.autograd.Function):
+    """weight_norm'd Conv1d weight (g [O,1,1], v [O,I,Kw]) -> packed [O, Kw*I] (tcn.py:19-24)."""
+
+    @staticmethod
+    def forward(ctx, g, v):
+        _chk(g, v)
+        O, I, Kw = v.shape
+        w = torch.empty((O, Kw * I), device=v.device, dtype=torch.float32)
+        norm = torch.empty((O,), device=v.device, dtype=torch.float32)
+        _call("ha2g_tcn_weight_fwd", _p(g), _p(v), _p(w), _p(norm), O, I, Kw, _st())
+        ctx.save_for_backward(g, v, norm)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        g, v, norm = ctx.saved_tensors
+        O, I, Kw = v.shape
+        dw = _c(dw)
+        dg = torch.zeros_like(g)
+        dv = torch.zeros_like(v)
+        _call("ha2g_tcn_weight_bwd", _p(dw), _p(g), _p(v), _p(norm), _p(dg), _p(dv), O, I, Kw, _st())
+        return dg, dv
+
+
+def tcn_weight(g, v):
+    return _TcnWeightFn.apply(g, v)
+
+
+class _ShiftConcatFn(torch.autograd.Function):
+    """[x(t-d) | x(t)] staging of a causal dilated k=2 conv (tcn.py:19-21 + Chomp1d)."""
+
+    @staticmethod
+    def forward(ctx, x, d):
+        x = _c(x)
+        _chk(x)
+        B, T, C = x.shape
+        out = torch.empty((B, T, 2 * C), device=x.device, dtype=torch.float32)
+        _call("ha2g_shift_concat_fwd", _p(x), _p(out), B, T, C, d, _st())
+        ctx.d = d
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _c(dout)
+        B, T, C2 = dout.shape
+        dx = torch.empty((B, T, C2 // 2), device=dout.device, dtype=torch.float32)
+        _call("ha2g_shift_concat_bwd", _p(dout), _p(dx), B, T, C2 // 2, ctx.d, _st())
+        return dx, None
+
+
+def shift_concat(x, d):
+    return _ShiftConcatFn.apply(x, d)
+
+
+# ------------------------------------------------------------------------------------------------
+# cascade glue
+# ------------------------------------------------------------------------------------------------
+def gather_cols(src: torch.Tensor, idx_i32: torch.Tensor) -> torch.Tensor:
+    """src[..., idx] (no gradient: used for the target_k bone subsets)."""
+    src = _c(src)
+    _chk(src)
+    rows = src.numel() // src.shape[-1]
+    n = idx_i32.numel()
+    out = torch.empty((*src.shape[:-1], n), device=src.device, dtype=torch.float32)
+    _call("ha2g_gather_cols", _p(src), src.shape[-1], _p(idx_i32), n, _p(out), n, rows, _st())
+    return out
+
+
+class _PreSeqFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, target_k, prev_out, slot_src, src_slot, n_pre):
+        target_k = _c(target_k)
+        _chk(target_k, prev_out)
+        B, T, d = target_k.shape
+        pre = torch.empty((B, T, d + 1), device=target_k.device, dtype=torch.float32)
+        dp = 0
+        if prev_out is not None:
+            prev_out = _c(prev_out)
+            dp = prev_out.shape[2]
+        _call("ha2g_pre_seq_fwd", _p(target_k), _p(prev_out), dp, _p(slot_src), _p(pre), B, T, d, n_pre, _st())
+        ctx.cfg = (B, T, d, dp, n_pre)
+        ctx.src_slot = src_slot
+        return pre
+
+    @staticmethod
+    def backward(ctx, dpre):
+        B, T, d, dp, n_pre = ctx.cfg
+        if dp == 0 or not ctx.needs_input_grad[1]:
+            return None, None, None, None, None
+        dpre = _c(dpre)
+        dprev = torch.empty((B, T, dp), device=dpre.device, dtype=torch.float32)
+        _call("ha2g_pre_seq_bwd", _p(dpre), d + 1, _p(ctx.src_slot), _p(dprev), B, T, dp, n_pre, _st())
+        return None, dprev, None, None, None
+
+
+def pre_seq(target_k, prev_out, slot_src, src_slot, n_pre):
+    return _PreSeqFn.apply(target_k, prev_out, slot_src, src_slot, n_pre)
+
+
+# ------------------------------------------------------------------------------------------------
+# Conv1d (valid) as unfold + GEMM, BatchNorm over [rows, C]
+# ------------------------------------------------------------------------------------------------
+class _Unfold1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kw):
+        x = _c(x)
+        _chk(x)
+        B, T, C = x.shape
+        out = torch.empty((B, T - kw + 1, kw * C), device=x.device, dtype=torch.float32)
+        _call("ha2g_unfold1d_fwd", _p(x), _p(out), B, T, C, kw, _st())
+        ctx.cfg = (B, T, C, kw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, C, kw = ctx.cfg
+        dout = _c(dout)
+        dx = torch.empty((B, T, C), device=dout.device, dtype=torch.float32)
+        _call("ha2g_unfold1d_bwd", _p(dout), _p(dx), B, T, C, kw, _st())
+        return dx, None
+
+
+class _PackConv1dWFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w):
+        _chk(w)
+        O, I, Kw = w.shape
+        wp = torch.empty((O, Kw * I), device=w.device, dtype=torch.float32)
+        _call("ha2g_pack_conv1d_w", _p(w), _p(wp), O, I, Kw, 0, _st())
+        ctx.shape = (O, I, Kw)
+        return wp
+
+    @staticmethod
+    def backward(ctx, dwp):
+        O, I, Kw = ctx.shape
+        dwp = _c(dwp)
+        dw = torch.empty((O, I, Kw), device=dwp.device, dtype=torch.float32)
+        _call("ha2g_pack_conv1d_w", _p(dwp), _p(dw), O, I, Kw, 1, _st())
+        return dw
+
+
+def conv1d_valid(x, w, b, act=ACT_NONE):
+    """nn.Conv1d(C_in, C_out, Kw) on a [B,T,C_in] (channels-last) sequence -> [B,T-Kw+1,C_out]."""
+    kw = w.shape[2]
+    return linear(_Unfold1dFn.apply(x, kw), _PackConv1dWFn.apply(w), b, act)
+
+
+class _BNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rm, rv, pre_relu, post_act, training, eps, momentum):
+        x = _c(x)
+        _chk(x, gamma, beta, rm, rv)
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dev = x.device
+        mean = torch.empty((C,), device=dev, dtype=torch.float32)
+        invstd = torch.empty((C,), device=dev, dtype=torch.float32)
+        sums = torch.empty((2 * C,), device=dev, dtype=torch.float64)
+        y = torch.empty_like(x)
+        _call("ha2g_bn_fwd", _p(x), rows, C, int(pre_relu), post_act, int(training), _p(gamma), _p(beta), _p(rm), _p(rv),
+              eps, momentum, _p(mean), _p(invstd), _p(sums), _p(y), _st())
+        ctx.cfg = (rows, C, int(pre_relu), post_act, training)
+        ctx.save_for_backward(x, y if post_act else None, gamma, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        rows, C, pre_relu, post_act, training = ctx.cfg
+        if not training:
+            raise RuntimeError("BatchNorm backward is only implemented for training mode (batch statistics)")
+        x, y, gamma, mean, invstd = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        dg = torch.zeros_like(gamma)
+        db = torch.zeros_like(gamma)
+        sums = torch.empty((2 * C,), device=dy.device, dtype=torch.float64)
+        _call("ha2g_bn_bwd", _p(dy), _p(x), _p(y), rows, C, pre_relu, post_act, _p(gamma), _p(mean), _p(invstd), _p(sums),
+              _p(dx), _p(dg), _p(db), _st())
+        return dx, dg, db, None, None, None, None, None, None, None
+
+
+def batch_norm(x, gamma, beta, running_mean, running_var, pre_relu=False, post_act=ACT_NONE, training=True,
+               eps=1e-5, momentum=0.1):
+    """BatchNorm over the last (channel) axis of a channels-last tensor; see csrc/bn.cu."""
+    return _BNFn.apply(x, gamma, beta, running_mean, running_var, pre_relu, post_act, training, eps, momentum)

@@ -1,0 +1,213 @@
+"""Differentiable ops of the ResNetSE-34 audio encoder (channels-last / NHWC), backed by
+csrc/conv2d.cu, csrc/bn.cu and csrc/audio.cu.  See ha2g_b200/ops.py for the conventions."""
+from __future__ import annotations
+
+import torch
+
+from .ops import _c, _call, _chk, _p, _st
+
+
+class _Conv2dFn(torch.autograd.Function):
+    """nn.Conv2d on NHWC activations; weight stays in the checkpoint layout OIHW."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad):
+        x = _c(x)
+        _chk(x, w, b)
+        N, H, W, Cin = x.shape
+        Cout, _, KH, KW = w.shape
+        Ho = (H + 2 * pad - KH) // stride + 1
+        Wo = (W + 2 * pad - KW) // stride + 1
+        wf = torch.empty((KH * KW * Cin, Cout), device=x.device, dtype=torch.float32)
+        _call("ha2g_conv2d_pack", _p(w), _p(wf), Cout, Cin, KH, KW, 0, _st())
+        y = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+        _call("ha2g_conv2d_fwd", _p(x), _p(wf), _p(b), _p(y), N, H, W, Cin, Cout, KH, KW, stride, pad, 0, _st())
+        ctx.cfg = (N, H, W, Cin, Cout, KH, KW, stride, pad)
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, Cin, Cout, KH, KW, stride, pad = ctx.cfg
+        x, w = ctx.saved_tensors
+        dy = _c(dy)
+        dev = dy.device
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wb = torch.empty((KH * KW * Cout, Cin), device=dev, dtype=torch.float32)
+            _call("ha2g_conv2d_pack", _p(w), _p(wb), Cout, Cin, KH, KW, 1, _st())
+            dx = torch.empty((N, H, W, Cin), device=dev, dtype=torch.float32)
+            _call("ha2g_conv2d_dgrad", _p(dy), _p(wb), _p(dx), N, H, W, Cin, Cout, KH, KW, stride, pad, _st())
+        if ctx.needs_input_grad[1]:
+            dwf = torch.zeros((KH * KW * Cin, Cout), device=dev, dtype=torch.float32)
+            _call("ha2g_conv2d_wgrad", _p(x), _p(dy), _p(dwf), N, H, W, Cin, Cout, KH, KW, stride, pad, _st())
+            dw = torch.empty_like(w)
+            _call("ha2g_conv2d_pack", _p(dwf), _p(dw), Cout, Cin, KH, KW, 2, _st())
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros((Cout,), device=dev, dtype=torch.float32)
+            rows = dy.numel() // Cout
+            _call("ha2g_col_sum", _p(dy), rows, Cout, Cout, _p(db), _st())
+        return dx, dw, db, None, None
+
+
+def conv2d(x, w, b=None, stride=1, pad=0):
+    return _Conv2dFn.apply(x, w, b, stride, pad)
+
+
+class _StemConvFn(torch.autograd.Function):
+    """Conv2d(1, C, 3, padding=1) on the (B,128,70) log-mel image (ResNetSE34V2.py:27,125)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _c(x)
+        _chk(x, w, b)
+        N, H, W = x.shape
+        Cout = w.shape[0]
+        y = torch.empty((N, H, W, Cout), device=x.device, dtype=torch.float32)
+        _call("ha2g_stem_conv_fwd", _p(x), _p(w), _p(b), _p(y), N, H, W, Cout, _st())
+        ctx.save_for_backward(x)
+        ctx.cfg = (N, H, W, Cout)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        N, H, W, Cout = ctx.cfg
+        dy = _c(dy)
+        dw = torch.zeros((Cout, 1, 3, 3), device=dy.device, dtype=torch.float32)
+        db = torch.zeros((Cout,), device=dy.device, dtype=torch.float32)
+        _call("ha2g_stem_conv_wgrad", _p(x), _p(dy), _p(dw), _p(db), N, H, W, Cout, _st())
+        return None, dw, db  # the spectrogram is an input, never differentiated
+
+
+def stem_conv(x, w, b):
+    return _StemConvFn.apply(x, w, b)
+
+
+class _SEFn(torch.autograd.Function):
+    """out = relu(u * sigmoid(W2 relu(W1 gap(u) + b1) + b2) + res)   (ResNetBlocks.py:29-37,81-96)."""
+
+    @staticmethod
+    def forward(ctx, u, res, w1, b1, w2, b2):
+        u, res = _c(u), _c(res)
+        _chk(u, res, w1, b1, w2, b2)
+        N, H, W, C = u.shape
+        R = w1.shape[0]
+        dev = u.device
+        gap = torch.empty((N, C), device=dev, dtype=torch.float32)
+        h = torch.empty((N, R), device=dev, dtype=torch.float32)
+        s = torch.empty((N, C), device=dev, dtype=torch.float32)
+        out = torch.empty_like(u)
+        _call("ha2g_se_fwd", _p(u), _p(res), _p(w1), _p(b1), _p(w2), _p(b2), _p(gap), _p(h), _p(s), _p(out), N, H * W, C, R,
+              _st())
+        ctx.cfg = (N, H * W, C, R)
+        ctx.save_for_backward(u, out, gap, h, s, w1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, HW, C, R = ctx.cfg
+        u, out, gap, h, s, w1, w2 = ctx.saved_tensors
+        dout = _c(dout)
+        dev = dout.device
+        dres = torch.empty_like(u)
+        du = torch.empty_like(u)
+        ds = torch.empty((N, C), device=dev, dtype=torch.float32)
+        dgap = torch.empty((N, C), device=dev, dtype=torch.float32)
+        dw1 = torch.zeros_like(w1)
+        db1 = torch.zeros((R,), device=dev, dtype=torch.float32)
+        dw2 = torch.zeros_like(w2)
+        db2 = torch.zeros((C,), device=dev, dtype=torch.float32)
+        _call("ha2g_se_bwd", _p(dout), _p(out), _p(u), _p(gap), _p(h), _p(s), _p(w1), _p(w2), _p(dres), _p(du), _p(ds),
+              _p(dgap), _p(dw1), _p(db1), _p(dw2), _p(db2), N, HW, C, R, _st())
+        return du, dres, dw1, db1, dw2, db2
+
+
+def se_residual_relu(u, res, w1, b1, w2, b2):
+    return _SEFn.apply(u, res, w1, b1, w2, b2)
+
+
+class _PixelShuffleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, r):
+        x = _c(x)
+        _chk(x)
+        N, H, W, C = x.shape
+        Co = C // (r * r)
+        y = torch.empty((N, H * r, W * r, Co), device=x.device, dtype=torch.float32)
+        _call("ha2g_pixel_shuffle", _p(x), _p(y), N, H, W, Co, r, 0, _st())
+        ctx.cfg = (N, H, W, Co, r)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, Co, r = ctx.cfg
+        dy = _c(dy)
+        dx = torch.empty((N, H, W, Co * r * r), device=dy.device, dtype=torch.float32)
+        _call("ha2g_pixel_shuffle", _p(dy), _p(dx), N, H, W, Co, r, 1, _st())
+        return dx, None
+
+
+def pixel_shuffle(x, r):
+    return _PixelShuffleFn.apply(x, r)
+
+
+class _HeadFlattenFn(torch.autograd.Function):
+    """[N,F,T,C] (NHWC) -> [N,T,C*F] with feature index c*F+f (ResNetSE34V2.py:160-162)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        _chk(x)
+        N, F, T, C = x.shape
+        y = torch.empty((N, T, C * F), device=x.device, dtype=torch.float32)
+        _call("ha2g_head_flatten", _p(x), _p(y), N, F, T, C, 0, _st())
+        ctx.cfg = (N, F, T, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, F, T, C = ctx.cfg
+        dy = _c(dy)
+        dx = torch.empty((N, F, T, C), device=dy.device, dtype=torch.float32)
+        _call("ha2g_head_flatten", _p(dy), _p(dx), N, F, T, C, 1, _st())
+        return dx
+
+
+def head_flatten(x):
+    return _HeadFlattenFn.apply(x)
+
+
+class _BlendFn(torch.autograd.Function):
+    """softmax over the 3 levels + L weighted sums (ResNetSE34V2.py:202-212)."""
+
+    @staticmethod
+    def forward(ctx, logits, f0, f1, f2, L):
+        logits, f0, f1, f2 = _c(logits), _c(f0), _c(f1), _c(f2)
+        _chk(logits, f0, f1, f2)
+        B = f0.shape[0]
+        TC = f0.numel() // B
+        weight = torch.empty((B, 3, L), device=f0.device, dtype=torch.float32)
+        blend = torch.empty((L, *f0.shape), device=f0.device, dtype=torch.float32)
+        _call("ha2g_blend_fwd", _p(logits), _p(f0), _p(f1), _p(f2), _p(weight), _p(blend), B, TC, L, _st())
+        ctx.cfg = (B, TC, L)
+        ctx.save_for_backward(weight, f0, f1, f2)
+        return weight, blend
+
+    @staticmethod
+    def backward(ctx, dweight, dblend):
+        B, TC, L = ctx.cfg
+        weight, f0, f1, f2 = ctx.saved_tensors
+        dev = f0.device
+        dblend = _c(dblend) if dblend is not None else torch.zeros((L, *f0.shape), device=dev, dtype=torch.float32)
+        dweight = _c(dweight) if dweight is not None else None
+        df0, df1, df2 = torch.empty_like(f0), torch.empty_like(f1), torch.empty_like(f2)
+        dlogits = torch.empty((B, 3 * L), device=dev, dtype=torch.float32)
+        _call("ha2g_blend_bwd", _p(weight), _p(f0), _p(f1), _p(f2), _p(dweight), _p(dblend), _p(df0), _p(df1), _p(df2),
+              _p(dlogits), B, TC, L, _st())
+        return dlogits, df0, df1, df2, None
+
+
+def speaker_blend(logits, f0, f1, f2, L):
+    return _BlendFn.apply(logits, f0, f1, f2, L)

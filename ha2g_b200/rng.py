@@ -1,0 +1,73 @@
+"""Random draws of the HA2G step, behind one injectable source.
+
+The reference step consumes randomness in three places: ``reparameterize`` noise
+(scripts/model/embedding_net.py:10-13, one (B,16) draw per generator call, also in eval mode),
+dropout masks (embedding 0.1, TCN 0.3, GRU inter-layer 0.3) and the speaker ``torch.randperm``
+(scripts/train_eval/train_hierarchy_expressive.py:328).  cuDNN's dropout stream is not reproducible,
+so the reference is only defined up to these draws; parity tests inject them.
+
+Default source: torch's CUDA generator (device-side Philox; plumbing, not a product kernel).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Callable, List, Optional
+
+import torch
+
+_state = {"dropout": True, "randn": None, "mask": None, "randperm": None}
+
+
+def dropout_enabled() -> bool:
+    return _state["dropout"]
+
+
+def randn(shape, device) -> torch.Tensor:
+    if _state["randn"] is not None:
+        return _state["randn"](tuple(shape)).to(device=device, dtype=torch.float32).contiguous()
+    return torch.randn(tuple(shape), device=device, dtype=torch.float32)
+
+
+def dropout_mask(shape, p: float, device) -> torch.Tensor:
+    """float32 {0,1} keep-mask with P(keep) = 1-p."""
+    if _state["mask"] is not None:
+        return _state["mask"](tuple(shape), p).to(device=device, dtype=torch.float32).contiguous()
+    return (torch.rand(tuple(shape), device=device) >= p).to(torch.float32)
+
+
+def randperm(n: int, device) -> torch.Tensor:
+    if _state["randperm"] is not None:
+        return _state["randperm"](n).to(device)
+    return torch.randperm(n, device=device)
+
+
+@contextlib.contextmanager
+def override(randn_fn: Optional[Callable] = None, mask_fn: Optional[Callable] = None,
+             randperm_fn: Optional[Callable] = None, dropout: Optional[bool] = None):
+    """Inject deterministic draws (tests) or switch dropout off (parity with the no-dropout goldens)."""
+    old = dict(_state)
+    if randn_fn is not None:
+        _state["randn"] = randn_fn
+    if mask_fn is not None:
+        _state["mask"] = mask_fn
+    if randperm_fn is not None:
+        _state["randperm"] = randperm_fn
+    if dropout is not None:
+        _state["dropout"] = dropout
+    try:
+        yield
+    finally:
+        _state.update(old)
+
+
+class ListFeed:
+    """randn_fn that replays a fixed list of tensors in call order."""
+
+    def __init__(self, tensors: List[torch.Tensor]):
+        self.tensors, self.i = list(tensors), 0
+
+    def __call__(self, shape):
+        t = self.tensors[self.i]
+        self.i += 1
+        assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+        return t

@@ -1,0 +1,146 @@
+"""One HA2G hierarchical training step on a B200, shared by both dataset variants.
+
+Mirrors ``train_iter_hierarchy`` (scripts/train_eval/train_hierarchy.py:71-293, 3 levels) and
+``train_iter_hierarchy_expressive`` (scripts/train_eval/train_hierarchy_expressive.py:124-483, 6 levels):
+same call order of the modules, the same losses and weights, the same RNG draws in the same order,
+the same optimizer steps and the same returned dict of python floats.  Differences are purely
+mechanical and result-preserving:
+  * the two cascades whose outputs the reference detaches (D-step, random-speaker pass) run under
+    ``torch.no_grad`` (no BPTT state is saved for them);
+  * the discriminator's parameters do not accumulate gradient during the generator step (the reference
+    computes then discards those gradients: dis_optimizer.zero_grad() precedes the next use);
+  * loss terms are back-propagated as several roots with constant weights instead of being summed into
+    one scalar first (identical gradients, no scalar arithmetic kernels);
+  * all ``.item()`` reads are packed into a single device->host copy at the end of the step.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List
+
+import torch
+
+from .. import cascade, ops_loss, rng
+from ..optim import fused_adam_step, zero_grad
+
+
+@contextlib.contextmanager
+def _frozen(module):
+    flags = [(p, p.requires_grad) for p in module.parameters()]
+    for p, _ in flags:
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p, f in flags:
+            p.requires_grad_(f)
+
+
+def _w(value: float, like: torch.Tensor) -> torch.Tensor:
+    return torch.full((1,), float(value), device=like.device, dtype=torch.float32)
+
+
+def train_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_indices, gens: List, discriminator,
+               audio_encoder, text_encoder, gen_optimizers: List, dis_optimizer, audio_optimizer, text_optimizer
+               ) -> Dict[str, float]:
+    warm_up_epochs = args.loss_warmup
+    n_pre = args.n_pre_poses
+    dev = target.device
+
+    weight, feat_low, feat_mid, feat_high, linear_blend_feat = audio_encoder(in_spec, vid_indices)
+    text_feat = text_encoder(in_text_padded)
+    targets = cascade.split_targets(variant, target)
+
+    scalars: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ train D
+    gan_on = epoch > warm_up_epochs and args.loss_gan_weight > 0.0
+    if gan_on:
+        zero_grad(dis_optimizer)
+        with torch.no_grad():
+            outs_d, _ = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat, vid_indices, n_pre)
+        dis_real = discriminator(target, in_text_padded)
+        dis_fake = discriminator(outs_d[-1].detach(), in_text_padded)
+        l_real = ops_loss.neg_mean_log(dis_real)
+        l_fake = ops_loss.neg_mean_log1m(dis_fake)
+        one = _w(1.0, target)
+        torch.autograd.backward([l_real, l_fake], [one, one])
+        fused_adam_step(dis_optimizer)
+        scalars["dis_real"], scalars["dis_fake"] = l_real.detach(), l_fake.detach()
+
+    # ------------------------------------------------------------------ train G
+    for opt in gen_optimizers:
+        zero_grad(opt)
+    zero_grad(audio_optimizer)
+    zero_grad(text_optimizer)
+
+    roots, root_w = [], []
+
+    def add(name, t, w):
+        scalars[name] = t.detach()
+        if w != 0.0:
+            roots.append(t)
+            root_w.append(_w(w, t))
+
+    tf = text_feat.reshape(-1, text_feat.shape[2])
+    if args.loss_contrastive_pos_weight > 0.0:
+        add("c_pos", ops_loss.contrastive(tf, feat_high.reshape(-1, feat_high.shape[2]), variant),
+            args.loss_contrastive_pos_weight)
+    if args.loss_contrastive_neg_weight > 0.0:  # text_low_contrastive = -criterion(...)
+        add("c_neg", ops_loss.contrastive(tf, feat_low.reshape(-1, feat_low.shape[2]), variant),
+            -args.loss_contrastive_neg_weight)
+
+    outs, (z_context, z_mu, z_logvar) = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat,
+                                                            vid_indices, n_pre)
+    out_dir_vec = outs[-1]
+    for k, (o, t) in enumerate(zip(outs, targets)):
+        add(f"huber{k}", ops_loss.huber(o, t, 0.1), args.loss_regression_weight)
+
+    with _frozen(discriminator):
+        dis_output = discriminator(out_dir_vec, in_text_padded)
+    add("gen", ops_loss.neg_mean_log(dis_output), args.loss_gan_weight if epoch > warm_up_epochs else 0.0)
+
+    use_reg = (args.z_type == "speaker" or args.z_type == "random") and args.loss_reg_weight > 0.0
+    if use_reg:
+        if args.z_type != "speaker":
+            raise NotImplementedError("z_type='random' is not on the hierarchy configs' path")
+        rand_idx = rng.randperm(vid_indices.shape[0], vid_indices.device)
+        rand_vids = vid_indices[rand_idx]
+        with torch.no_grad():
+            outs_r, (z_context_rand, _, _) = cascade.run_cascade(variant, gens, targets, in_text_padded,
+                                                                 linear_blend_feat, rand_vids, n_pre)
+        add("div_reg", ops_loss.div_reg(out_dir_vec, outs_r[-1], z_context, z_context_rand, 0.05), args.loss_reg_weight)
+        add("kld", ops_loss.kld(z_mu, z_logvar), args.loss_kld_weight)
+
+    if args.loss_physical_weight > 0.0:
+        mdv = [float(v[0]) if isinstance(v, (list, tuple)) else float(v) for v in args.mean_dir_vec]
+        add("phy", ops_loss.physical(out_dir_vec, variant, mdv), args.loss_physical_weight)
+
+    torch.autograd.backward(roots, root_w)
+
+    for opt in gen_optimizers:
+        fused_adam_step(opt)
+    fused_adam_step(audio_optimizer)
+    fused_adam_step(text_optimizer)
+
+    # ------------------------------------------------------------------ one packed device->host read
+    names = list(scalars.keys())
+    vals = torch.cat([scalars[n].reshape(1) for n in names]).tolist()
+    v = dict(zip(names, vals))
+    huber_loss = sum(v[f"huber{k}"] for k in range(len(outs)))
+    ret_dict = {"loss": args.loss_regression_weight * huber_loss}
+    if use_reg:
+        if v["kld"]:
+            ret_dict["KLD"] = args.loss_kld_weight * v["kld"]
+        if v["div_reg"]:
+            ret_dict["DIV_REG"] = args.loss_reg_weight * v["div_reg"]
+    if gan_on:
+        ret_dict["gen"] = args.loss_gan_weight * v["gen"]
+        ret_dict["dis"] = v["dis_real"] + v["dis_fake"]
+    if args.loss_contrastive_pos_weight > 0.0:
+        ret_dict["c_pos"] = args.loss_contrastive_pos_weight * v["c_pos"]
+    if args.loss_contrastive_neg_weight > 0.0:
+        ret_dict["c_neg"] = args.loss_contrastive_neg_weight * (-v["c_neg"])
+    if args.loss_physical_weight > 0.0:
+        ret_dict["phy"] = args.loss_physical_weight * v["phy"]
+    return ret_dict

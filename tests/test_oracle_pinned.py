@@ -1,0 +1,177 @@
+"""Pins oracle/ha2g_oracle.py against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py -> tests/golden/*.pt).  CPU only."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import ha2g_oracle as O  # noqa: E402
+
+from ha2g_b200 import constants as K  # noqa: E402
+from ha2g_b200.constants import make_args  # noqa: E402
+from ha2g_b200.model.hierarchy_net import (Hierarchical_ConvDiscriminator, Hierarchical_PoseGenerator,  # noqa: E402
+                                           Hierarchical_WavEncoder, TextEncoderTCN)
+from ha2g_b200.model.vocab import make_speaker_vocab  # noqa: E402
+from ha2g_b200.synthetic import det_fill, make_batch, make_embedding  # noqa: E402
+from helpers import AUDIO_GRAD_TOL, assert_close, assert_params_close, assert_summary_close, build_modules, randn, sd_cpu, summary_scale  # noqa: E402
+
+
+def _leaf(sd):
+    return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
+            for k, v in sd.items()}
+
+
+def _check_grads(sd, gold_grads, what, tol=1e-3):
+    floor = summary_scale(gold_grads.values())
+    for name, summ in gold_grads.items():
+        assert sd[name].grad is not None, f"{what}: no grad for {name}"
+        assert_summary_close(sd[name].grad, summ, f"{what}.{name}", tol, floor=floor)
+
+
+def _setup(g):
+    args = make_args("expressive")
+    spk = make_speaker_vocab(g["n_spk"])
+    emb = make_embedding(g["n_words"], 300, 1).numpy()
+    batch = make_batch("expressive", g["B"], g["n_words"], g["n_spk"], seed=g["batch_seed"])
+    return args, spk, emb, batch
+
+
+def test_text_encoder(golden_modules):
+    g = golden_modules
+    args, spk, emb, batch = _setup(g)
+    m = det_fill(TextEncoderTCN(args, g["n_words"], 300, pre_trained_embedding=emb, dropout=0.3), g["text"]["fill_seed"])
+    sd = _leaf(sd_cpu(m))
+    out = O.text_encoder_tcn(batch["in_text_padded"], sd)
+    assert_close(out, g["text"]["out"], "text.out", 1e-5)
+    (out * randn(out.shape, 5, "gout_text")).sum().backward()
+    _check_grads(sd, g["text"]["grads"], "text")
+
+
+@pytest.mark.parametrize("tag,d", [("gen126", 126), ("gen15", 15)])
+def test_generator(golden_modules, tag, d):
+    g = golden_modules
+    args, spk, emb, batch = _setup(g)
+    m = det_fill(Hierarchical_PoseGenerator(args, d, g["n_words"], 300, emb, z_obj=spk), g[tag]["fill_seed"])
+    sd = _leaf(sd_cpu(m))
+    B = g["B"]
+    pre = (randn((B, 34, d + 1), 5, "pre" + tag) * 0.1).requires_grad_(True)
+    aud = randn((B, 34, 32), 5, "aud" + tag).requires_grad_(True)
+    eps = randn((B, 16), 7, "eps0")
+    out, z, mu, lv = O.pose_generator(sd, pre, batch["in_text_padded"], aud, batch["vid"], eps)
+    for a, b, n in ((out, g[tag]["out"], "out"), (z, g[tag]["z"], "z"), (mu, g[tag]["mu"], "mu"), (lv, g[tag]["logvar"], "lv")):
+        assert_close(a, b, f"{tag}.{n}", 1e-4)
+    gout = randn(out.shape, 5, "gout" + tag)
+    ((out * gout).sum() + z.sum() * 0.3 + (mu * mu).sum() * 0.2 + lv.sum() * 0.1).backward()
+    assert_close(pre.grad, g[tag]["dpre"], f"{tag}.dpre", 1e-4)
+    assert_close(aud.grad, g[tag]["daud"], f"{tag}.daud", 1e-4)
+    _check_grads(sd, g[tag]["grads"], tag)
+
+
+def test_discriminator(golden_modules):
+    g = golden_modules
+    args, spk, emb, batch = _setup(g)
+    m = det_fill(Hierarchical_ConvDiscriminator(126), g["dis"]["fill_seed"])
+    sd = _leaf(sd_cpu(m))
+    poses = batch["target"].clone().requires_grad_(True)
+    stats = {}
+    out = O.conv_discriminator(sd, poses, True, stats)
+    assert_close(out, g["dis"]["out"], "dis.out", 1e-4)
+    (out * randn(out.shape, 5, "gout_dis")).sum().backward()
+    assert_close(poses.grad, g["dis"]["dposes"], "dis.dposes", 1e-4)
+    _check_grads(sd, g["dis"]["grads"], "dis")
+    for k, v in stats.items():
+        assert_close(v.float(), g["dis"]["buffers"][k].float(), f"dis.{k}", 1e-5)
+    sd2 = dict(sd_cpu(m)); sd2.update(stats)
+    assert_close(O.conv_discriminator(sd2, batch["target"], False), g["dis"]["out_eval"], "dis.eval", 1e-4)
+
+
+def test_audio_encoder(golden_modules):
+    g = golden_modules
+    args, spk, emb, batch = _setup(g)
+    m = det_fill(Hierarchical_WavEncoder(args, spk, pose_level=6, nOut=32), g["audio"]["fill_seed"])
+    sd = _leaf(sd_cpu(m))
+    stats = {}
+    w, fl, fm, fh, blend = O.wav_encoder(sd, batch["in_spec"], batch["vid"], 6, True, stats)
+    ga = g["audio"]
+    for a, b, n in ((w, ga["weight"], "weight"), (fl, ga["feat_low"], "low"), (fm, ga["feat_mid"], "mid"), (fh, ga["feat_high"], "high")):
+        assert_close(a, b, f"audio.{n}", 1e-4)
+    for i in range(6):
+        assert_close(blend[i], ga["blend"][i], f"audio.blend{i}", 1e-4)
+    loss = 0
+    for i, t in enumerate([w, fl, fm, fh] + blend):
+        loss = loss + (t * randn(t.shape, 5, f"gout_aud{i}")).sum()
+    loss.backward()
+    _check_grads(sd, ga["grads"], "audio", AUDIO_GRAD_TOL)
+    for k, v in stats.items():
+        assert_summary_close(v.float(), ga["buffers"][k], f"audio.{k}", 1e-4)
+
+
+@pytest.mark.parametrize("variant", ["gesture", "expressive"])
+def test_contrastive(golden_modules, variant):
+    g = golden_modules["contrastive_" + variant]
+    a = randn((68, 32), 5, "ca").requires_grad_(True)
+    b = randn((68, 32), 5, "cb").requires_grad_(True)
+    l = O.contrastive_loss(a, b, variant)
+    assert_close(l, g["loss"], "contrastive.loss", 1e-5)
+    l.backward()
+    assert_close(a.grad, g["da"], "contrastive.da", 1e-4)
+    assert_close(b.grad, g["db"], "contrastive.db", 1e-4)
+
+
+def _tables(variant):
+    if variant == "expressive":
+        return {"pairs": K.EXPRESSIVE_ANGLE_PAIR, "avg": K.EXPRESSIVE_AVG_ANGLE, "var": K.EXPRESSIVE_VAR_ANGLE}
+    return {"pairs": K.GESTURE_ANGLE_PAIR, "avg": K.GESTURE_AVG_ANGLE, "var": K.GESTURE_VAR_ANGLE}
+
+
+@pytest.mark.parametrize("variant", ["gesture", "expressive"])
+def test_train_step(golden_steps, variant):
+    """Three consecutive reference steps (epoch 0, 11, 11): losses, gradients, post-Adam parameters, BN buffers."""
+    g = golden_steps[variant]
+    args, gens, D, A, T = build_modules(variant, g["n_words"], g["n_spk"], g["fill_seeds"])
+    state = {"gens": [sd_cpu(m) for m in gens], "dis": sd_cpu(D), "audio": sd_cpu(A), "text": sd_cpu(T)}
+    opt_state = {}
+    for step, rec in enumerate(g["steps"]):
+        batch = make_batch(variant, g["B"], g["n_words"], g["n_spk"], seed=rec["batch_seed"])
+        L = len(gens)
+        n = 0
+        eps = {}
+        for key in (["d"] if rec["epoch"] > args.loss_warmup else []) + ["g", "r"]:
+            eps[key] = [randn((g["B"], 16), rec["eps_seed"], f"eps{n + i}") for i in range(L)]
+            n += L
+        ret, state, grads = O.train_step(variant, args, rec["epoch"], batch["in_text_padded"], batch["in_spec"],
+                                         batch["target"], batch["vid"], state["gens"], state["dis"], state["audio"],
+                                         state["text"], opt_state, eps, rec["perm"], _tables(variant))
+        assert set(ret) == set(rec["ret"]), (ret.keys(), rec["ret"].keys())
+        for k in rec["ret"]:
+            # step 0: 1e-3 (north_star).  Later steps start from parameters that went through Adam's sign-like
+            # first update, which amplifies fp32 noise into O(lr) parameter differences -> 3e-3.
+            tol = (1e-3, 3e-3, 2e-2)[step]
+            assert abs(ret[k] - rec["ret"][k]) <= tol * max(1.0, abs(rec["ret"][k])), (step, k, ret[k], rec["ret"][k])
+        if "grads" in rec:
+            for fam, mine in (("g_last", grads["gens"][-1]), ("audio", grads["audio"]), ("text", grads["text"])):
+                floor = summary_scale(rec["grads"][fam].values())
+                for name, summ in rec["grads"][fam].items():
+                    assert_summary_close(mine[name], summ, f"step{step}.{fam}.{name}",
+                                         AUDIO_GRAD_TOL if fam == "audio" else 2e-3, floor=floor)
+        # post-step parameters (Adam-normalised updates: see helpers.assert_params_close) and BN buffers
+        for tag, sds, golds, lr in (("gens", state["gens"], rec["gens"], args.learning_rate),
+                                    ("dis", [state["dis"]], [rec["dis"]], args.learning_rate * args.discriminator_lr_weight),
+                                    ("audio", [state["audio"]], [rec["audio"]], args.learning_rate),
+                                    ("text", [state["text"]], [rec["text"]], args.learning_rate)):
+            for i, (sd, gold) in enumerate(zip(sds, golds)):
+                for name, summ in gold.items():
+                    if name not in sd:
+                        continue
+                    if "running_" in name or "num_batches" in name:
+                        assert_summary_close(sd[name].float(), summ, f"step{step}.{tag}{i}.{name}", (1e-3, 3e-3, 2e-2)[step])
+                    else:
+                        # Conv1d biases feeding a train-mode BatchNorm have an exactly-zero true gradient: their
+                        # Adam updates are pure rounding-noise signs in the reference too -> only the bound applies.
+                        # From the second step on, trajectories have decorrelated at the O(lr) level (sign flips of
+                        # step 0 feed a train-mode-BN network), so only the movement bound is asserted there.
+                        noise_only = tag == "dis" and name in ("pre_conv.0.bias", "pre_conv.3.bias")
+                        assert_params_close(sd[name], summ, f"step{step}.{tag}{i}.{name}", lr, step + 1,
+                                            1.0 if (noise_only or step > 0) else (0.10 if tag == "audio" else 0.02))
