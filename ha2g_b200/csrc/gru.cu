@@ -148,7 +148,11 @@ __global__ void gru_gates_bwd_kernel(const float* __restrict__ dy, int dy_ld, in
 
 #define HA2G_CHECK(call) do { int e_ = (call); if (e_ != 0) return e_; } while (0)
 
-// Forward of one bidirectional layer: gi = x W_ih^T + b_ih (two GEMMs), then T fused step launches.
+// Forward of ONE bidirectional nn.GRU layer (replaces the cuDNN RNN call behind `self.gru(in_data, None)`,
+// scripts/model/hierarchy_net.py:144 generator / :232 discriminator): gi = x W_ih^T + b_ih (two GEMMs),
+// then T fused "h W_hh^T + gates" step launches covering both directions.
+//   x [M,T,I];  w_ih_* [3H,I], w_hh_* [3H,H], b_* [3H] (gate order r,z,n; *_f forward, *_r reverse direction)
+//   gi [M,T,2,3H] scratch/out;  y [M,T,2H] out;  gates [M,T,2,4H] out (nullptr = inference, nothing saved)
 HA2G_API int ha2g_gru_layer_fwd(const float* x, int I, const float* w_ih_f, const float* w_ih_r, const float* b_ih_f,
                                 const float* b_ih_r, const float* w_hh_f, const float* w_hh_r, const float* b_hh_f,
                                 const float* b_hh_r, float* gi, float* y, float* gates, int M, int T, int H,

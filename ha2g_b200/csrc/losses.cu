@@ -386,8 +386,6 @@ HA2G_API int ha2g_physical(const float* out, float* grad, int64_t rows, int vari
     physical_kernel<<<ha2g_div_up(rows, 4), 128, 0, stream>>>(out, grad, rows, variant, nb, npairs, loss);
     HA2G_RETURN_LAST();
 }
-// Contrastive forward.  a, b: [N,32].  Outputs: an, bn [N,32], na, nb [N] (normalised rows + norms), lse [N],
-// loss ACCUMULATED.  scratch: part [N * ceil(N/128) * 2] floats (upper bound), diag [N].
 static int contrastive_splits(int N) {
     int rows_ctas = (N + CT - 1) / CT;
     int s = (148 * 2 + rows_ctas - 1) / rows_ctas;
@@ -396,6 +394,12 @@ static int contrastive_splits(int N) {
     if (s < 1) s = 1;
     return s;
 }
+// Streaming SoftmaxContrastiveLoss forward (replaces criterion(text_feat, feat_*) at
+// scripts/train_eval/train_hierarchy_expressive.py:244-249; class at train_hierarchy.py:23-68): L2-normalise rows,
+// logits = 1/pairwise-distance (variant 0 gesture: 1/(D+1e-8) clamped at 1e-8; variant 1 expressive: 1/D),
+// cross-entropy against the diagonal -- tiled with an online log-sum-exp, the N x N x 32 tensor is never built.
+// a, b: [N,32].  Outputs: an, bn [N,32], na, nb [N] (normalised rows + norms), lse [N]; loss ACCUMULATED.
+// scratch: part [N * ceil(N/128) * 2] floats (upper bound), diag [N].
 HA2G_API int ha2g_contrastive_fwd(const float* a, const float* b, float* an, float* bn, float* na, float* nb, float* lse,
                                   float* part, float* diag, int N, int variant, float* loss, cudaStream_t stream) {
     const int S = contrastive_splits(N);

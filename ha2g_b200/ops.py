@@ -42,9 +42,35 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_prof = {"on": False, "only": None, "flops_fn": None, "recs": {}}
+
+
 def _call(name: str, *args):
     LAUNCHES[0] += 1
+    if _prof["on"] and (_prof["only"] is None or _prof["only"] == name):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        getattr(lib, name)(*args)
+        e1.record()
+        fl = _prof["flops_fn"](name, args) if _prof["flops_fn"] is not None else 0.0
+        _prof["recs"].setdefault(name, []).append((e0, e1, fl))
+        return
     getattr(lib, name)(*args)
+
+
+def profile_begin(all_launchers: bool = False, only: Optional[str] = None, flops_fn=None):
+    """Time C-ABI launcher calls with CUDA events on the launching stream (bench.py's roofline leg)."""
+    _prof.update(on=bool(all_launchers or only), only=None if all_launchers else only, flops_fn=flops_fn, recs={})
+
+
+def profile_end():
+    """-> {launcher: {"ms": total device time, "calls": n, "flops": algorithmic FLOPs}}"""
+    torch.cuda.synchronize()
+    out = {}
+    for name, recs in _prof["recs"].items():
+        out[name] = {"ms": sum(a.elapsed_time(b) for a, b, _ in recs), "calls": len(recs), "flops": sum(f for _, _, f in recs)}
+    _prof.update(on=False, only=None, flops_fn=None, recs={})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -309,7 +335,7 @@ class _BiGRUFn(torch.autograd.Function):
         x = _c(x)
         _chk(x, *weights)
         M, T, _ = x.shape
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights))
+        need_grad = any(ctx.needs_input_grad)  # (grad mode is off inside Function.forward)
         saved: List[torch.Tensor] = []
         masks = []
         cur = x

@@ -78,6 +78,6 @@ def det_fill(module: torch.nn.Module, seed: int = 0) -> torch.nn.Module:
 
 def sample_tensor(t: torch.Tensor, n: int = 256):
     """(norm, strided sample) summary of a tensor for compact golden storage."""
-    f = t.detach().reshape(-1).double()
+    f = t.detach().cpu().reshape(-1).double()
     stride = max(1, f.numel() // n)
     return {"norm": float(f.norm()), "numel": f.numel(), "stride": stride, "sample": f[::stride][:n].float().clone()}

@@ -20,7 +20,7 @@ from typing import Dict, List
 
 import torch
 
-from .. import cascade, ops_loss, rng
+from .. import cascade, dp, ops_loss, rng
 from ..optim import fused_adam_step, zero_grad
 
 
@@ -65,6 +65,7 @@ def train_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_i
         l_fake = ops_loss.neg_mean_log1m(dis_fake)
         one = _w(1.0, target)
         torch.autograd.backward([l_real, l_fake], [one, one])
+        dp.allreduce_grads(dis_optimizer)
         fused_adam_step(dis_optimizer)
         scalars["dis_real"], scalars["dis_fake"] = l_real.detach(), l_fake.detach()
 
@@ -118,10 +119,9 @@ def train_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_i
 
     torch.autograd.backward(roots, root_w)
 
-    for opt in gen_optimizers:
+    for opt in list(gen_optimizers) + [audio_optimizer, text_optimizer]:
+        dp.allreduce_grads(opt)   # no-op on one GPU
         fused_adam_step(opt)
-    fused_adam_step(audio_optimizer)
-    fused_adam_step(text_optimizer)
 
     # ------------------------------------------------------------------ one packed device->host read
     names = list(scalars.keys())

@@ -1,0 +1,338 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden fixtures produced by the unmodified
+reference, and against the CPU oracle on seeded inputs.  Run on the B200 box: pytest -m gpu."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+
+from ha2g_b200 import constants as K  # noqa: E402
+from ha2g_b200 import rng  # noqa: E402
+from ha2g_b200.constants import make_args  # noqa: E402
+from ha2g_b200.model.hierarchy_net import (Hierarchical_ConvDiscriminator, Hierarchical_PoseGenerator,  # noqa: E402
+                                           Hierarchical_WavEncoder, TextEncoderTCN)
+from ha2g_b200.model.vocab import make_speaker_vocab  # noqa: E402
+from ha2g_b200.synthetic import det_fill, make_batch, make_embedding  # noqa: E402
+from helpers import (AUDIO_GRAD_TOL, assert_close, assert_params_close, assert_summary_close, build_modules, randn,  # noqa: E402
+                     sd_cpu, summary_scale)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _check_grads(m, gold_grads, what, tol=1e-3):
+    floor = summary_scale(gold_grads.values())
+    named = dict(m.named_parameters())
+    errs = []
+    for name, summ in gold_grads.items():
+        assert named[name].grad is not None, f"{what}: no grad for {name}"
+        try:
+            assert_summary_close(named[name].grad, summ, f"{what}.{name}", tol, floor=floor)
+        except AssertionError as e:
+            errs.append(str(e))
+    assert not errs, "\n".join(errs[:12]) + f"\n({len(errs)} tensors out of tolerance)"
+
+
+def _setup(g):
+    args = make_args("expressive")
+    spk = make_speaker_vocab(g["n_spk"])
+    emb = make_embedding(g["n_words"], 300, 1).numpy()
+    batch = make_batch("expressive", g["B"], g["n_words"], g["n_spk"], seed=g["batch_seed"])
+    return args, spk, emb, {k: v.to(DEV) for k, v in batch.items()}
+
+
+def test_gemm_variants():
+    """All four transpose modes, ragged sizes, bias/activation, accumulate and split-K of ha2g_gemm_f32."""
+    from ha2g_b200 import ops
+    torch.manual_seed(0)
+    for (M, N, K) in [(1, 1, 1), (37, 29, 53), (128, 64, 16), (300, 900, 300), (130, 70, 1000)]:
+        for tA in (0, 1):
+            for tB in (0, 1):
+                A = torch.randn((K, M) if tA else (M, K))
+                B = torch.randn((N, K) if tB else (K, N))
+                bias = torch.randn(N)
+                ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + bias.double()
+                C = torch.zeros((M, N), device=DEV)
+                ops.gemm(A.to(DEV), B.to(DEV), C, bias.to(DEV), M, N, K, A.shape[1], B.shape[1], N, tA, tB, 0, 0, 1)
+                assert_close(C, ref, f"gemm {M}x{N}x{K} tA={tA} tB={tB}", 1e-5)
+                C2 = torch.ones((M, N), device=DEV)
+                ops.gemm(A.to(DEV), B.to(DEV), C2, None, M, N, K, A.shape[1], B.shape[1], N, tA, tB, 0, 1, 4)
+                assert_close(C2, ref - bias.double() + 1.0, f"gemm split-K {M}x{N}x{K} tA={tA} tB={tB}", 1e-5)
+    x = torch.randn(50, 40)
+    w = torch.randn(30, 40)
+    y = torch.empty((50, 30), device=DEV)
+    ops.gemm(x.to(DEV), w.to(DEV), y, None, 50, 30, 40, 40, 40, 30, 0, 1, 2, 0, 1)
+    assert_close(y, torch.nn.functional.leaky_relu(x @ w.t(), 0.01), "gemm lrelu epilogue", 1e-5)
+
+
+def test_gru_layer_vs_torch():
+    """ha2g_gru_layer_fwd/bwd against torch.nn.GRU (CPU) for H=300 (generator) and H=64 (discriminator)."""
+    from ha2g_b200 import ops
+    for (M, T, I, H, L) in [(3, 34, 105, 300, 2), (5, 28, 8, 64, 4), (33, 7, 20, 16, 1)]:
+        torch.manual_seed(1)
+        gru = torch.nn.GRU(I, H, L, batch_first=True, bidirectional=True)
+        x = torch.randn(M, T, I, requires_grad=True)
+        y, _ = gru(x)
+        g = torch.randn_like(y)
+        (y * g).sum().backward()
+        ws = [p.detach().to(DEV).requires_grad_(True) for p in gru._flat_weights]
+        xd = x.detach().to(DEV).requires_grad_(True)
+        yd = ops.bigru(xd, ws, H, L, 0.0, True, sum_dirs=False)
+        assert_close(yd, y, f"gru fwd H={H}", 1e-4)
+        (yd * g.to(DEV)).sum().backward()
+        assert_close(xd.grad, x.grad, f"gru dx H={H}", 1e-3)
+        for w, p, name in zip(ws, gru._flat_weights, gru._flat_weights_names):
+            assert_close(w.grad, p.grad, f"gru d{name} H={H}", 1e-3)
+
+
+def test_text_encoder(golden_modules):
+    g = golden_modules
+    args, spk, emb, batch = _setup(g)
+    m = det_fill(TextEncoderTCN(args, g["n_words"], 300, pre_trained_embedding=emb, dropout=0.3), g["text"]["fill_seed"]).to(DEV)
+    with rng.override(dropout=False):
+        out = m(batch["in_text_padded"])
+        assert_close(out, g["text"]["out"], "text.out")
+        (out * randn(out.shape, 5, "gout_text").to(DEV)).sum().backward()
+    _check_grads(m, g["text"]["grads"], "text")
+
+
+@pytest.mark.parametrize("tag,d", [("gen126", 126), ("gen15", 15)])
+def test_generator(golden_modules, tag, d):
+    g = golden_modules
+    args, spk, emb, batch = _setup(g)
+    m = det_fill(Hierarchical_PoseGenerator(args, d, g["n_words"], 300, emb, z_obj=spk), g[tag]["fill_seed"]).to(DEV)
+    B = g["B"]
+    pre = (randn((B, 34, d + 1), 5, "pre" + tag) * 0.1).to(DEV).requires_grad_(True)
+    aud = randn((B, 34, 32), 5, "aud" + tag).to(DEV).requires_grad_(True)
+    with rng.override(randn_fn=rng.ListFeed([randn((B, 16), 7, "eps0")]), dropout=False):
+        out, z, mu, lv = m(pre, batch["in_text_padded"], aud, batch["vid"])
+    for a, b, n in ((out, g[tag]["out"], "out"), (z, g[tag]["z"], "z"), (mu, g[tag]["mu"], "mu"), (lv, g[tag]["logvar"], "lv")):
+        assert_close(a, b, f"{tag}.{n}")
+    gout = randn(out.shape, 5, "gout" + tag).to(DEV)
+    # scalar glue of the test objective uses torch ops; the module's own forward/backward is all ours
+    ((out * gout).sum() + z.sum() * 0.3 + (mu * mu).sum() * 0.2 + lv.sum() * 0.1).backward()
+    assert_close(pre.grad, g[tag]["dpre"], f"{tag}.dpre")
+    assert_close(aud.grad, g[tag]["daud"], f"{tag}.daud")
+    _check_grads(m, g[tag]["grads"], tag)
+
+
+def test_discriminator(golden_modules):
+    g = golden_modules
+    args, spk, emb, batch = _setup(g)
+    m = det_fill(Hierarchical_ConvDiscriminator(126), g["dis"]["fill_seed"]).to(DEV)
+    poses = batch["target"].clone().requires_grad_(True)
+    with rng.override(dropout=False):
+        out = m(poses)
+    assert_close(out, g["dis"]["out"], "dis.out")
+    (out * randn(out.shape, 5, "gout_dis").to(DEV)).sum().backward()
+    assert_close(poses.grad, g["dis"]["dposes"], "dis.dposes")
+    _check_grads(m, g["dis"]["grads"], "dis")
+    for k, v in m.named_buffers():
+        assert_close(v.float(), g["dis"]["buffers"][k].float(), f"dis.{k}", 1e-4)
+    m.eval()
+    with torch.no_grad():
+        assert_close(m(batch["target"]), g["dis"]["out_eval"], "dis.eval")
+
+
+def test_audio_encoder(golden_modules):
+    g = golden_modules
+    args, spk, emb, batch = _setup(g)
+    m = det_fill(Hierarchical_WavEncoder(args, spk, pose_level=6, nOut=32), g["audio"]["fill_seed"]).to(DEV)
+    ga = g["audio"]
+    w, fl, fm, fh, blend = m(batch["in_spec"], batch["vid"])
+    for a, b, n in ((w, ga["weight"], "weight"), (fl, ga["feat_low"], "low"), (fm, ga["feat_mid"], "mid"), (fh, ga["feat_high"], "high")):
+        assert_close(a, b, f"audio.{n}")
+    for i in range(6):
+        assert_close(blend[i], ga["blend"][i], f"audio.blend{i}")
+    loss = 0
+    for i, t in enumerate([w, fl, fm, fh] + blend):
+        loss = loss + (t * randn(t.shape, 5, f"gout_aud{i}").to(DEV)).sum()
+    loss.backward()
+    _check_grads(m, ga["grads"], "audio", AUDIO_GRAD_TOL)
+    for k, v in m.named_buffers():
+        assert_summary_close(v.float(), ga["buffers"][k], f"audio.{k}", 1e-3)
+    m.eval()
+    with torch.no_grad():
+        w, fl, fm, fh, blend = m(batch["in_spec"], batch["vid"])
+    for a, b, n in ((w, ga["eval"]["weight"], "weight"), (fl, ga["eval"]["feat_low"], "low"), (fh, ga["eval"]["feat_high"], "high"),
+                    (blend[5], ga["eval"]["blend5"], "blend5")):
+        assert_close(a, b, f"audio.eval.{n}")
+
+
+@pytest.mark.parametrize("variant", ["gesture", "expressive"])
+def test_contrastive(golden_modules, variant):
+    from ha2g_b200 import ops_loss
+    g = golden_modules["contrastive_" + variant]
+    a = randn((68, 32), 5, "ca").to(DEV).requires_grad_(True)
+    b = randn((68, 32), 5, "cb").to(DEV).requires_grad_(True)
+    l = ops_loss.contrastive(a, b, variant)
+    assert_close(l, g["loss"], "contrastive.loss", 1e-4)
+    l.backward(torch.ones(1, device=DEV))
+    assert_close(a.grad, g["da"], "contrastive.da")
+    assert_close(b.grad, g["db"], "contrastive.db")
+
+
+def test_contrastive_large_vs_oracle():
+    """N = 128*34 rows (BASELINE config 2/3 size) against the oracle's N x N formulation computed blockwise in fp64."""
+    import ha2g_oracle as O
+    from ha2g_b200 import ops_loss
+    N = 1500
+    a = randn((N, 32), 9, "cla")
+    b = randn((N, 32), 9, "clb")
+    for variant in ("gesture", "expressive"):
+        ad, bd = a.double().requires_grad_(True), b.double().requires_grad_(True)
+        lo = O.contrastive_loss(ad, bd, variant)
+        lo.backward()
+        ag, bg = a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        l = ops_loss.contrastive(ag, bg, variant)
+        l.backward(torch.ones(1, device=DEV))
+        assert_close(l, lo, f"contrastive N={N} {variant}", 1e-4)
+        assert_close(ag.grad, ad.grad, f"contrastive N={N} {variant} da")
+        assert_close(bg.grad, bd.grad, f"contrastive N={N} {variant} db")
+
+
+@pytest.mark.parametrize("variant", ["gesture", "expressive"])
+def test_losses_vs_oracle(variant):
+    import ha2g_oracle as O
+    from ha2g_b200 import ops_loss
+    args = make_args(variant)
+    D = 126 if variant == "expressive" else 27
+    B = 5
+    out = (randn((B, 34, D), 3, "lo") * 0.3)
+    tgt = randn((B, 34, D), 3, "lt") * 0.1
+    outr = randn((B, 34, D), 3, "lr") * 0.3
+    z, zr = randn((B, 16), 3, "z"), randn((B, 16), 3, "zr")
+    mu, lv = randn((B, 16), 3, "mu"), randn((B, 16), 3, "lv") * 0.3
+    mdv = torch.tensor([v[0] for v in args.mean_dir_vec])
+    tabs = ({"pairs": K.EXPRESSIVE_ANGLE_PAIR, "avg": K.EXPRESSIVE_AVG_ANGLE, "var": K.EXPRESSIVE_VAR_ANGLE} if variant == "expressive"
+            else {"pairs": K.GESTURE_ANGLE_PAIR, "avg": K.GESTURE_AVG_ANGLE, "var": K.GESTURE_VAR_ANGLE})
+    one = torch.ones(1, device=DEV)
+
+    def both(name, f_oracle, f_cuda, inputs, tol=1e-3):
+        cpu_in = [t.clone().double().requires_grad_(True) for t in inputs]
+        lo = f_oracle(*cpu_in)
+        lo.backward()
+        gpu_in = [t.to(DEV).requires_grad_(True) for t in inputs]
+        l = f_cuda(*gpu_in)
+        l.backward(one)
+        assert_close(l, lo, f"{variant}.{name}", 1e-4)
+        for i, (a, b) in enumerate(zip(gpu_in, cpu_in)):
+            if b.grad is not None:
+                assert_close(a.grad, b.grad, f"{variant}.{name}.grad{i}", tol)
+
+    both("huber", lambda o: O.huber_sum([o], [tgt.double()]), lambda o: ops_loss.huber(o, tgt.to(DEV), 0.1), [out])
+    both("div_reg", lambda o: O.div_reg_loss(o, outr.double(), z.double(), zr.double()),
+         lambda o: ops_loss.div_reg(o, outr.to(DEV), z.to(DEV), zr.to(DEV)), [out])
+    both("kld", O.kld_loss, ops_loss.kld, [mu, lv])
+    both("physical", lambda o: O.physical_loss(o, mdv.double(), variant, tabs["pairs"], tabs["avg"], tabs["var"]),
+         lambda o: ops_loss.physical(o, variant, [float(v) for v in mdv]), [out], 2e-3)
+    p = torch.rand((B, 1), generator=torch.Generator().manual_seed(1)) * 0.9 + 0.05
+    both("gan_real", lambda x: -torch.mean(torch.log(x + 1e-8)), ops_loss.neg_mean_log, [p])
+    both("gan_fake", lambda x: -torch.mean(torch.log(1 - x + 1e-8)), ops_loss.neg_mean_log1m, [p])
+
+
+def test_cascade_tables_bit_exact():
+    """pre_seq / target gathers on the GPU equal the oracle's index arithmetic exactly (index path: bit-exact)."""
+    import ha2g_oracle as O
+    from ha2g_b200 import cascade, ops
+    for variant in ("gesture", "expressive"):
+        D = 126 if variant == "expressive" else 27
+        tgt = randn((3, 34, D), 4, "ct")
+        chans = O.level_channels(variant)
+        maps = O.cascade_maps(variant)
+        tks = cascade.split_targets(variant, tgt.to(DEV))
+        tabs = cascade.device_tables(variant, torch.device(DEV))
+        prev = None
+        for k, c in enumerate(chans):
+            tk = tgt[:, :, torch.as_tensor(c)]
+            assert torch.equal(tks[k].cpu(), tk), f"{variant} target_{k + 1}"
+            pre_o = O.make_pre_seq(tk, prev, maps[k], 4)
+            pre_g = ops.pre_seq(tks[k], None if prev is None else prev.to(DEV), tabs[k][1], tabs[k][2], 4)
+            assert torch.equal(pre_g.cpu(), pre_o), f"{variant} pre_seq_{k + 1}"
+            prev = randn((3, 34, len(c)), 4, f"prev{k}")
+
+
+def test_fused_adam_matches_torch():
+    from ha2g_b200.optim import fused_adam_step
+    torch.manual_seed(0)
+    ps = [torch.randn(s) for s in [(7,), (300, 300), (1, 33), (70001,)]]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    mine = [p.clone().to(DEV).requires_grad_(True) for p in ps]
+    o_ref = torch.optim.Adam(ref, lr=5e-4, betas=(0.5, 0.999))
+    o_mine = torch.optim.Adam(mine, lr=5e-4, betas=(0.5, 0.999))
+    for it in range(3):
+        for r, m in zip(ref, mine):
+            g = torch.randn(r.shape, generator=torch.Generator().manual_seed(it * 10 + r.numel() % 7))
+            r.grad = g.clone()
+            m.grad = g.clone().to(DEV)
+        o_ref.step()
+        fused_adam_step(o_mine)
+        for r, m in zip(ref, mine):
+            assert_close(m, r, f"adam step {it}", 1e-6)
+    sd = o_mine.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+@pytest.mark.parametrize("variant", ["gesture", "expressive"])
+def test_train_step_vs_reference(golden_steps, variant):
+    """The first reference step (epoch 0) and the first GAN step (epoch 11) of train_iter_hierarchy*: returned loss
+    dict, gradients and post-Adam parameters against the fixtures from the unmodified reference."""
+    from ha2g_b200.train_eval.train_hierarchy import train_iter_hierarchy
+    from ha2g_b200.train_eval.train_hierarchy_expressive import train_iter_hierarchy_expressive
+    g = golden_steps[variant]
+    args, gens, D, A, T = build_modules(variant, g["n_words"], g["n_spk"], g["fill_seeds"], DEV)
+    lr = args.learning_rate
+    mk = lambda m, l=lr: torch.optim.Adam(m.parameters(), lr=l, betas=(0.5, 0.999))
+    gopts, dopt, aopt, topt = [mk(x) for x in gens], mk(D, lr * args.discriminator_lr_weight), mk(A), mk(T)
+    fn = train_iter_hierarchy if variant == "gesture" else train_iter_hierarchy_expressive
+    L = len(gens)
+    for step, rec in enumerate(g["steps"]):
+        batch = {k: v.to(DEV) for k, v in make_batch(variant, g["B"], g["n_words"], g["n_spk"], seed=rec["batch_seed"]).items()}
+        n_draws = (3 if rec["epoch"] > args.loss_warmup else 2) * L
+        feed = rng.ListFeed([randn((g["B"], 16), rec["eps_seed"], f"eps{i}") for i in range(n_draws)])
+        captured = {}
+        if step == 0:
+            # capture gradients just before the optimizer steps
+            import ha2g_b200.train_eval._step as S
+            orig = S.fused_adam_step
+
+            def spy(opt):
+                for grp in opt.param_groups:
+                    for p in grp["params"]:
+                        if p.grad is not None:
+                            captured[id(p)] = p.grad.detach().clone()
+                orig(opt)
+            S.fused_adam_step = spy
+        try:
+            with rng.override(randn_fn=feed, randperm_fn=lambda n, p=rec["perm"]: p.clone(), dropout=False):
+                ret = fn(args, rec["epoch"], batch["in_text_padded"], batch["in_spec"], batch["target"], batch["vid"],
+                         *gens, D, A, T, *gopts, dopt, aopt, topt)
+        finally:
+            if step == 0:
+                S.fused_adam_step = orig
+        assert set(ret) == set(rec["ret"]), (sorted(ret), sorted(rec["ret"]))
+        tol = (1e-3, 3e-3, 2e-2)[step]
+        bad = {k: (ret[k], rec["ret"][k]) for k in ret if abs(ret[k] - rec["ret"][k]) > tol * max(1.0, abs(rec["ret"][k]))}
+        assert not bad, f"step {step} loss dict mismatch (mine, reference): {bad}"
+        if step == 0:
+            for fam, mod, gtol in (("g_last", gens[-1], 2e-3), ("g_first", gens[0], 2e-3), ("audio", A, AUDIO_GRAD_TOL), ("text", T, 2e-3)):
+                floor = summary_scale(rec["grads"][fam].values())
+                named = dict(mod.named_parameters())
+                errs = []
+                for name, summ in rec["grads"][fam].items():
+                    try:
+                        assert_summary_close(captured[id(named[name])], summ, f"step0.{fam}.{name}", gtol, floor=floor)
+                    except AssertionError as e:
+                        errs.append(str(e))
+                assert not errs, "\n".join(errs[:10]) + f"\n({len(errs)} gradient tensors out of tolerance)"
+            for tag, mods, golds, l in (("gens", gens, rec["gens"], lr), ("dis", [D], [rec["dis"]], lr * args.discriminator_lr_weight),
+                                        ("audio", [A], [rec["audio"]], lr), ("text", [T], [rec["text"]], lr)):
+                for i, (m, gold) in enumerate(zip(mods, golds)):
+                    sd = m.state_dict()
+                    for name, summ in gold.items():
+                        if "running_" in name or "num_batches" in name:
+                            assert_summary_close(sd[name].float(), summ, f"step0.{tag}{i}.{name}", 1e-3)
+                        else:
+                            assert_params_close(sd[name], summ, f"step0.{tag}{i}.{name}", l, 1, 0.10 if tag == "audio" else 0.02)
