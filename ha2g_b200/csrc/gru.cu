@@ -21,6 +21,23 @@ extern "C" int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* o
 extern "C" int ha2g_gemm_f32_kseg(const float*, const float*, float*, const float*, int, int, int, int, int, int, int,
                                   int, int, int, int, int, int, cudaStream_t);
 
+extern "C" int ha2g_gru_cluster_supported(int H, int* ok);
+extern "C" int ha2g_gru_seq_fwd_cluster(const float*, const float*, const float*, const float*, const float*, float*, float*,
+                                        int, int, int, cudaStream_t);
+extern "C" int ha2g_gru_seq_bwd_cluster(const float*, int, int, const float*, const float*, const float*, const float*,
+                                        float*, float*, int, int, int, cudaStream_t);
+#include <cstdlib>
+#include <cstring>
+
+// HA2G_GRU_IMPL=step forces the per-step kernels of this file (A/B testing); default: persistent cluster kernels.
+static bool use_cluster_path(int H) {
+    const char* e = getenv("HA2G_GRU_IMPL");
+    if (e != nullptr && strcmp(e, "step") == 0) return false;
+    int ok = 0;
+    ha2g_gru_cluster_supported(H, &ok);
+    return ok != 0;
+}
+
 namespace {
 
 constexpr int GR_ROWS = 32;   // batch rows per CTA
@@ -160,6 +177,7 @@ HA2G_API int ha2g_gru_layer_fwd(const float* x, int I, const float* w_ih_f, cons
     const int MT = M * T;
     HA2G_CHECK(ha2g_gemm_f32(x, w_ih_f, gi, b_ih_f, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
     HA2G_CHECK(ha2g_gemm_f32(x, w_ih_r, gi + 3 * H, b_ih_r, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
+    if (use_cluster_path(H)) return ha2g_gru_seq_fwd_cluster(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, stream);
     dim3 grid(ha2g_div_up(H, GR_HID), ha2g_div_up(M, GR_ROWS), 2);
     for (int s = 0; s < T; ++s) {
         gru_step_fwd_kernel<<<grid, GR_NT, 0, stream>>>(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, s);
@@ -182,15 +200,20 @@ HA2G_API int ha2g_gru_layer_bwd(const float* dy, int dy_ld, int dy_dir_stride, c
     cudaError_t ce = cudaMemsetAsync(dh_rec, 0, sizeof(float) * (size_t)M * 2 * H, stream);
     if (ce != cudaSuccess) return (int)ce;
     const int ew_grid = ha2g_ew_grid((int64_t)M * 2 * H, 256, 1);
-    for (int s = T - 1; s >= 0; --s) {
+    const bool clustered = use_cluster_path(H);
+    if (clustered)
+        HA2G_CHECK(ha2g_gru_seq_bwd_cluster(dy, dy_ld, dy_dir_stride, y, gates, w_hh_f, w_hh_r, dgi, dgh, M, T, H, stream));
+    for (int s = T - 1; s >= 0 && !clustered; --s) {
         gru_gates_bwd_kernel<<<ew_grid, 256, 0, stream>>>(dy, dy_ld, dy_dir_stride, y, gates, dgi, dgh, dh_rec, M, T, H, s);
         if (s > 0) {
             // dh_rec[m,dir,:] += dgh[m,t,dir,:] * W_hh_dir        ([M,3H] x [3H,H])
             const int tf = s, tr = T - 1 - s;
+            // (skinny: M x H outputs over K = 3H; split-K spreads it over the SMs until the cluster kernel takes over)
+            const int rsplit = H >= 256 ? 8 : 1;
             HA2G_CHECK(ha2g_gemm_f32(dgh + ((size_t)tf * 2 + 0) * 3 * H, w_hh_f, dh_rec, nullptr, M, H, 3 * H,
-                                     T * 6 * H, H, 2 * H, 0, 0, 0, 1, 1, stream));
+                                     T * 6 * H, H, 2 * H, 0, 0, 0, 1, rsplit, stream));
             HA2G_CHECK(ha2g_gemm_f32(dgh + ((size_t)tr * 2 + 1) * 3 * H, w_hh_r, dh_rec + H, nullptr, M, H, 3 * H,
-                                     T * 6 * H, H, 2 * H, 0, 0, 0, 1, 1, stream));
+                                     T * 6 * H, H, 2 * H, 0, 0, 0, 1, rsplit, stream));
         }
     }
     const int split = 4;

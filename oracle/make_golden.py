@@ -23,6 +23,36 @@ sys.modules.setdefault("fasttext", types.ModuleType("fasttext"))
 sys.path.insert(0, "/root/reference/scripts")
 warnings.filterwarnings("ignore")
 
+# Stub the third-party packages the reference's *drivers* import but this image lacks (none of them is on the
+# arithmetic path we pin; librosa's mel is replaced by oracle/mel_oracle.py, which is why row K stays "unpinned").
+import importlib.abc  # noqa: E402
+import importlib.machinery  # noqa: E402
+from unittest import mock  # noqa: E402
+
+_STUBS = ("librosa", "soundfile", "lmdb", "matplotlib", "mpl_toolkits", "configargparse", "umap", "tensorboardX",
+          "google", "gentle", "tensorboard", "torch.utils.tensorboard")
+
+
+class _StubLoader(importlib.abc.Loader):
+    def create_module(self, spec):
+        m = types.ModuleType(spec.name)
+        m.__path__ = []
+        m.__getattr__ = lambda name, _n=spec.name: mock.MagicMock(name=f"{_n}.{name}")
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+class _StubFinder(importlib.abc.MetaPathFinder):
+    def find_spec(self, name, path, target=None):
+        if name.split(".")[0] in _STUBS or name in _STUBS:
+            return importlib.machinery.ModuleSpec(name, _StubLoader(), is_package=True)
+        return None
+
+
+sys.meta_path.insert(0, _StubFinder())
+
 from model import vocab  # noqa: E402
 import model.embedding_net  # noqa: E402
 from model.hierarchy_net import (Hierarchical_ConvDiscriminator, Hierarchical_PoseGenerator,  # noqa: E402
@@ -204,9 +234,53 @@ def golden_keys():
     json.dump(out, open(os.path.join(OUT, "state_dict_keys.json"), "w"), indent=0)
 
 
+def golden_inference():
+    """generate_gestures_hierarchy (scripts/synthesize_expressive_hierarchy.py:36-259) UNMODIFIED, eval-mode modules,
+    6 s of synthetic audio (3 windows), with only librosa's mel swapped for oracle/mel_oracle.py."""
+    import pyarrow
+    if not hasattr(pyarrow, "serialize"):
+        pyarrow.serialize = pyarrow.deserialize = lambda *a, **k: None
+    import synthesize_expressive_hierarchy as S
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mel_oracle
+    from ha2g_b200.synthetic import make_audio
+    S.device = torch.device("cpu")
+    S.extract_melspectrogram = lambda audio, sr=16000: mel_oracle.extract_melspectrogram(audio)
+    args = make_args("expressive")
+    spk = speaker_vocab(N_SPK)
+    emb = make_embedding(N_WORDS, 300, 1).numpy()
+    lang = vocab.Vocab("words")
+    vocab_words = [f"w{i}" for i in range(N_WORDS - 4)]
+    for w in vocab_words:
+        lang.index_word(w)
+    assert lang.n_words == N_WORDS
+    dims = (24, 30, 36, 66, 96, 126)
+    gens = [det_fill(Hierarchical_PoseGenerator(args, d, N_WORDS, 300, emb.copy(), z_obj=spk), 70 + i).train(False)
+            for i, d in enumerate(dims)]
+    A = det_fill(Hierarchical_WavEncoder(args, spk, pose_level=6, nOut=32), 80).train(False)
+    audio = make_audio(96000, 5).numpy()
+    words = [[vocab_words[(7 * i) % len(vocab_words)], 0.3 + 0.37 * i, 0.3 + 0.37 * i + 0.25] for i in range(15)]
+    words.append(["not-in-vocab", 5.7, 5.9])
+    targets = [randn((1, 34, d), 81, f"t{d}") * 0.1 for d in dims]
+    model.embedding_net.reparameterize = EpsFeed(82, 1)
+    out = S.generate_gestures_hierarchy(args, *gens, A, lang, audio, words, *[t.clone() for t in targets], vid=2)
+    out_fade = None
+    model.embedding_net.reparameterize = EpsFeed(82, 1)
+    out_fade = S.generate_gestures_hierarchy(args, *gens, A, lang, audio, words, *[t.clone() for t in targets], vid=2,
+                                             fade_out=True)
+    torch.save({"out": torch.from_numpy(out), "out_fade": torch.from_numpy(out_fade), "n_words": N_WORDS, "n_spk": N_SPK,
+                "words": words, "vocab_words": vocab_words, "audio_seed": 5, "n_samples": 96000, "eps_seed": 82, "vid": 2,
+                "fill_seeds": {"gens": 70, "audio": 80}, "target_seed": 81}, os.path.join(OUT, "inference.pt"))
+    print("inference.pt written", out.shape, out_fade.shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     golden_keys()
+    if "--inference" in sys.argv:
+        golden_inference()
+        sys.exit(0)
     if "--keys" not in sys.argv:
         golden_modules()
         golden_steps()
+        golden_inference()
