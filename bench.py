@@ -85,7 +85,7 @@ class ClockSampler:
 # algorithmic work of the hot launchers (FLOPs from the call arguments; SURVEY.md 8(d) formulas)
 # ------------------------------------------------------------------------------------------------------------
 def launcher_flops(name, a):
-    if name == "ha2g_gemm_f32":
+    if name in ("ha2g_gemm_f32", "ha2g_gemm"):
         return 2.0 * a[4] * a[5] * a[6]
     if name == "ha2g_gru_layer_fwd":      # (x, I, ..., gi, y, gates, M, T, H, stream)
         I, M, T, H = a[1], a[13], a[14], a[15]

@@ -15,10 +15,10 @@
 // One launch per time step covers both directions (grid.z); h_{t-1} is read straight out of y.
 #include "common.cuh"
 
-extern "C" int ha2g_gemm_f32(const float*, const float*, float*, const float*, int, int, int, int, int, int, int, int,
+extern "C" int ha2g_gemm(const float*, const float*, float*, const float*, int, int, int, int, int, int, int, int,
                              int, int, int, cudaStream_t);
 extern "C" int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
-extern "C" int ha2g_gemm_f32_kseg(const float*, const float*, float*, const float*, int, int, int, int, int, int, int,
+extern "C" int ha2g_gemm_kseg(const float*, const float*, float*, const float*, int, int, int, int, int, int, int,
                                   int, int, int, int, int, int, cudaStream_t);
 
 extern "C" int ha2g_gru_cluster_supported(int H, int* ok);
@@ -175,8 +175,8 @@ HA2G_API int ha2g_gru_layer_fwd(const float* x, int I, const float* w_ih_f, cons
                                 const float* b_hh_r, float* gi, float* y, float* gates, int M, int T, int H,
                                 cudaStream_t stream) {
     const int MT = M * T;
-    HA2G_CHECK(ha2g_gemm_f32(x, w_ih_f, gi, b_ih_f, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
-    HA2G_CHECK(ha2g_gemm_f32(x, w_ih_r, gi + 3 * H, b_ih_r, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
+    HA2G_CHECK(ha2g_gemm(x, w_ih_f, gi, b_ih_f, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
+    HA2G_CHECK(ha2g_gemm(x, w_ih_r, gi + 3 * H, b_ih_r, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
     if (use_cluster_path(H)) return ha2g_gru_seq_fwd_cluster(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, stream);
     dim3 grid(ha2g_div_up(H, GR_HID), ha2g_div_up(M, GR_ROWS), 2);
     for (int s = 0; s < T; ++s) {
@@ -210,21 +210,21 @@ HA2G_API int ha2g_gru_layer_bwd(const float* dy, int dy_ld, int dy_dir_stride, c
             const int tf = s, tr = T - 1 - s;
             // (skinny: M x H outputs over K = 3H; split-K spreads it over the SMs until the cluster kernel takes over)
             const int rsplit = H >= 256 ? 8 : 1;
-            HA2G_CHECK(ha2g_gemm_f32(dgh + ((size_t)tf * 2 + 0) * 3 * H, w_hh_f, dh_rec, nullptr, M, H, 3 * H,
+            HA2G_CHECK(ha2g_gemm(dgh + ((size_t)tf * 2 + 0) * 3 * H, w_hh_f, dh_rec, nullptr, M, H, 3 * H,
                                      T * 6 * H, H, 2 * H, 0, 0, 0, 1, rsplit, stream));
-            HA2G_CHECK(ha2g_gemm_f32(dgh + ((size_t)tr * 2 + 1) * 3 * H, w_hh_r, dh_rec + H, nullptr, M, H, 3 * H,
+            HA2G_CHECK(ha2g_gemm(dgh + ((size_t)tr * 2 + 1) * 3 * H, w_hh_r, dh_rec + H, nullptr, M, H, 3 * H,
                                      T * 6 * H, H, 2 * H, 0, 0, 0, 1, rsplit, stream));
         }
     }
     const int split = 4;
     // dW_ih_dir += dgi[:,dir]^T x            ([3H, MT] x [MT, I])
-    HA2G_CHECK(ha2g_gemm_f32(dgi, x, dw_ih_f, nullptr, 3 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
-    HA2G_CHECK(ha2g_gemm_f32(dgi + 3 * H, x, dw_ih_r, nullptr, 3 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
+    HA2G_CHECK(ha2g_gemm(dgi, x, dw_ih_f, nullptr, 3 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
+    HA2G_CHECK(ha2g_gemm(dgi + 3 * H, x, dw_ih_r, nullptr, 3 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
     // dW_hh_f += sum_{m,t>=1} dgh[m,t,0]^T y[m,t-1,0:H];  dW_hh_r += sum_{m,t<=T-2} dgh[m,t,1]^T y[m,t+1,H:2H]
     if (T > 1) {
-        HA2G_CHECK(ha2g_gemm_f32_kseg(dgh + (size_t)6 * H, y, dw_hh_f, nullptr, 3 * H, H, M * (T - 1), 6 * H, 2 * H, H, 1,
+        HA2G_CHECK(ha2g_gemm_kseg(dgh + (size_t)6 * H, y, dw_hh_f, nullptr, 3 * H, H, M * (T - 1), 6 * H, 2 * H, H, 1,
                                       0, 0, 1, split, T - 1, T, stream));
-        HA2G_CHECK(ha2g_gemm_f32_kseg(dgh + 3 * H, y + (size_t)2 * H + H, dw_hh_r, nullptr, 3 * H, H, M * (T - 1), 6 * H,
+        HA2G_CHECK(ha2g_gemm_kseg(dgh + 3 * H, y + (size_t)2 * H + H, dw_hh_r, nullptr, 3 * H, H, M * (T - 1), 6 * H,
                                       2 * H, H, 1, 0, 0, 1, split, T - 1, T, stream));
     }
     // biases: column sums over all (m,t) rows
@@ -234,8 +234,8 @@ HA2G_API int ha2g_gru_layer_bwd(const float* dy, int dy_ld, int dy_dir_stride, c
     HA2G_CHECK(ha2g_col_sum(dgh + 3 * H, MT, 3 * H, 6 * H, db_hh_r, stream));
     // dx = dgi_f W_ih_f + dgi_r W_ih_r            ([MT,3H] x [3H,I])
     if (dx != nullptr) {
-        HA2G_CHECK(ha2g_gemm_f32(dgi, w_ih_f, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 0, 1, stream));
-        HA2G_CHECK(ha2g_gemm_f32(dgi + 3 * H, w_ih_r, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 1, 1, stream));
+        HA2G_CHECK(ha2g_gemm(dgi, w_ih_f, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 0, 1, stream));
+        HA2G_CHECK(ha2g_gemm(dgi + 3 * H, w_ih_r, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 1, 1, stream));
     }
     HA2G_RETURN_LAST();
 }

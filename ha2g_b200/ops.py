@@ -77,7 +77,18 @@ def profile_end():
 # raw helpers
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, tA=0, tB=0, act=0, acc=0, split=1):
-    _call("ha2g_gemm_f32", _p(A), _p(B), _p(C), _p(bias), M, N, K, lda, ldb, ldc, tA, tB, act, acc, split, _st())
+    _call("ha2g_gemm", _p(A), _p(B), _p(C), _p(bias), M, N, K, lda, ldb, ldc, tA, tB, act, acc, split, _st())
+
+
+def set_gemm_impl(impl: str):
+    """'auto' (default): packed tcgen05 bf16x3 GEMM for problems big enough to amortise packing, exact fp32 SIMT for
+    the small ones; 'f32': SIMT only; 'tc': register-staged tcgen05 kernel everywhere; 'tc2': packed kernel everywhere."""
+    lib.ha2g_set_gemm_impl({"f32": 0, "auto": 1, "tc": 2, "tc2": 3}[impl])
+
+
+def set_precision(mode: str):
+    """'fp32x3' (default): three-term bf16 split, fp32-accurate; 'bf16': plain bf16 operands on the tensor cores."""
+    lib.ha2g_set_gemm_terms(1 if mode == "bf16" else 3)
 
 
 def col_sum_into(x2d: torch.Tensor, out: torch.Tensor):

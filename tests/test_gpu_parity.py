@@ -43,28 +43,45 @@ def _setup(g):
     return args, spk, emb, {k: v.to(DEV) for k, v in batch.items()}
 
 
-def test_gemm_variants():
-    """All four transpose modes, ragged sizes, bias/activation, accumulate and split-K of ha2g_gemm_f32."""
+@pytest.mark.parametrize("impl,tol", [("f32", 1e-5), ("tc", 5e-5), ("tc2", 5e-5)])
+def test_gemm_variants(impl, tol):
+    """All four transpose modes, ragged sizes, unaligned leading dimensions, bias/activation, accumulate, split-K and the
+    segmented-K view, for the exact SIMT GEMM (gemm.cu) and the tcgen05 bf16x3 GEMM (gemm_tc.cu)."""
     from ha2g_b200 import ops
-    torch.manual_seed(0)
-    for (M, N, K) in [(1, 1, 1), (37, 29, 53), (128, 64, 16), (300, 900, 300), (130, 70, 1000)]:
-        for tA in (0, 1):
-            for tB in (0, 1):
-                A = torch.randn((K, M) if tA else (M, K))
-                B = torch.randn((N, K) if tB else (K, N))
-                bias = torch.randn(N)
-                ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + bias.double()
-                C = torch.zeros((M, N), device=DEV)
-                ops.gemm(A.to(DEV), B.to(DEV), C, bias.to(DEV), M, N, K, A.shape[1], B.shape[1], N, tA, tB, 0, 0, 1)
-                assert_close(C, ref, f"gemm {M}x{N}x{K} tA={tA} tB={tB}", 1e-5)
-                C2 = torch.ones((M, N), device=DEV)
-                ops.gemm(A.to(DEV), B.to(DEV), C2, None, M, N, K, A.shape[1], B.shape[1], N, tA, tB, 0, 1, 4)
-                assert_close(C2, ref - bias.double() + 1.0, f"gemm split-K {M}x{N}x{K} tA={tA} tB={tB}", 1e-5)
-    x = torch.randn(50, 40)
-    w = torch.randn(30, 40)
-    y = torch.empty((50, 30), device=DEV)
-    ops.gemm(x.to(DEV), w.to(DEV), y, None, 50, 30, 40, 40, 40, 30, 0, 1, 2, 0, 1)
-    assert_close(y, torch.nn.functional.leaky_relu(x @ w.t(), 0.01), "gemm lrelu epilogue", 1e-5)
+    from ha2g_b200.ops import _call, _p, _st
+    ops.set_gemm_impl(impl)
+    try:
+        torch.manual_seed(0)
+        for (M, N, K) in [(1, 1, 1), (37, 29, 53), (128, 64, 16), (300, 900, 300), (130, 70, 1000), (4352, 96, 207), (257, 40, 64)]:
+            for tA in (0, 1):
+                for tB in (0, 1):
+                    A = torch.randn((K, M) if tA else (M, K))
+                    B = torch.randn((N, K) if tB else (K, N))
+                    bias = torch.randn(N)
+                    ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + bias.double()
+                    C = torch.zeros((M, N), device=DEV)
+                    ops.gemm(A.to(DEV), B.to(DEV), C, bias.to(DEV), M, N, K, A.shape[1], B.shape[1], N, tA, tB, 0, 0, 1)
+                    assert_close(C, ref, f"{impl} gemm {M}x{N}x{K} tA={tA} tB={tB}", tol)
+                    C2 = torch.ones((M, N), device=DEV)
+                    ops.gemm(A.to(DEV), B.to(DEV), C2, None, M, N, K, A.shape[1], B.shape[1], N, tA, tB, 0, 1, 4)
+                    assert_close(C2, ref - bias.double() + 1.0, f"{impl} gemm split-K {M}x{N}x{K} tA={tA} tB={tB}", tol)
+        x = torch.randn(50, 40)
+        w = torch.randn(30, 40)
+        y = torch.empty((50, 30), device=DEV)
+        ops.gemm(x.to(DEV), w.to(DEV), y, None, 50, 30, 40, 40, 40, 30, 0, 1, 2, 0, 1)
+        assert_close(y, torch.nn.functional.leaky_relu(x @ w.t(), 0.01), f"{impl} gemm lrelu epilogue", tol)
+        # segmented reduction view (dW_hh of the GRU): rows (b, t<T-1) of [B*T, *] matrices, both operands K-leading
+        Bn, T, Mg, Ng = 5, 7, 33, 21
+        G = torch.randn(Bn * T, Mg)
+        Y = torch.randn(Bn * T, Ng)
+        ref = sum(G[b * T + 1:(b + 1) * T].double().t() @ Y[b * T:(b + 1) * T - 1].double() for b in range(Bn))
+        C = torch.zeros((Mg, Ng), device=DEV)
+        Gd, Yd = G.to(DEV), Y.to(DEV)
+        _call("ha2g_gemm_kseg", Gd.data_ptr() + 4 * Mg, _p(Yd), _p(C), None, Mg, Ng, Bn * (T - 1), Mg, Ng, Ng, 1, 0, 0, 1, 2,
+              T - 1, T, _st())
+        assert_close(C, ref, f"{impl} gemm kseg", tol)
+    finally:
+        ops.set_gemm_impl("auto")
 
 
 def test_gru_layer_vs_torch():
