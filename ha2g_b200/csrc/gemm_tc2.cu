@@ -20,7 +20,6 @@ namespace {
 
 constexpr int PBM = 128;   // UMMA_M
 constexpr int PBK = 32;    // K per stage (4 chunks of 8)
-constexpr int PST = 3;     // stages
 constexpr int PNT = 192;   // 6 warps
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,7 +118,10 @@ struct PSmem {
     static constexpr int A_BYTES = PBM * PBK * 2;
     static constexpr int B_BYTES = BN * PBK * 2;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TOTAL = PST * STAGE + 256;
+    // bytes in flight per SM are what hide the ~2 us loaded L2 latency: 192 KB either as 2 CTAs x 96 KB (BN <= 128) or as
+    // one CTA with four 48 KB stages (BN = 256, twice the MMA work per byte moved)
+    static constexpr int NSTAGE = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
+    static constexpr int TOTAL = NSTAGE * STAGE + 256;
 };
 
 template <int BN, int TERMS>
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
                                                           int stages_per_split) {
     extern __shared__ __align__(128) unsigned char smem[];
     using S = PSmem<BN>;
+    constexpr int PST = S::NSTAGE;
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + PST * S::STAGE);
     uint64_t* bar_empty = bar_full + PST;
     uint64_t* bar_done = bar_empty + PST;
@@ -237,19 +240,38 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
             }
             if (row < M) {
                 float* crow = C + (size_t)row * ldc;
+                const bool vec = !split && ((ldc & 3) == 0) && (n0 + c0 + 32 <= N) && ((((uintptr_t)C) & 15) == 0) &&
+                                 (bias == nullptr || (((uintptr_t)bias) & 15) == 0);
+                if (vec) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int col = n0 + c0 + i;
-                    if (col < N) {
-                        float v = __uint_as_float(r[i]);
-                        if (split) {
-                            if (bias != nullptr && blockIdx.z == 0) v += bias[col];
-                            atomicAdd(crow + col, v);
-                        } else {
-                            if (bias != nullptr) v += bias[col];
-                            v = ha2g_act(v, act);
-                            if (accumulate) v += crow[col];
-                            crow[col] = v;
+                    for (int i = 0; i < 32; i += 4) {
+                        const int col = n0 + c0 + i;
+                        float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                               __uint_as_float(r[i + 3]));
+                        if (bias != nullptr) {
+                            const float4 bv = *reinterpret_cast<const float4*>(bias + col);
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        }
+                        v.x = ha2g_act(v.x, act); v.y = ha2g_act(v.y, act); v.z = ha2g_act(v.z, act); v.w = ha2g_act(v.w, act);
+                        float4* dst = reinterpret_cast<float4*>(crow + col);
+                        if (accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        *dst = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = n0 + c0 + i;
+                        if (col < N) {
+                            float v = __uint_as_float(r[i]);
+                            if (split) {
+                                if (bias != nullptr && blockIdx.z == 0) v += bias[col];
+                                atomicAdd(crow + col, v);
+                            } else {
+                                if (bias != nullptr) v += bias[col];
+                                v = ha2g_act(v, act);
+                                if (accumulate) v += crow[col];
+                                crow[col] = v;
+                            }
                         }
                     }
                 }
@@ -286,10 +308,10 @@ static int launch_packed(const void* a_hi, const void* a_lo, int rows_pa, const 
 
 }  // namespace
 
-// Packed sizes of a [rows x K] operand: rows_p = rows rounded to 128, chunks_p = K/8 rounded to a multiple of 4;
+// Packed sizes of a [rows x K] operand: rows_p = rows rounded to 256, chunks_p = K/8 rounded to a multiple of 4;
 // each of hi / lo holds rows_p * chunks_p * 16 bytes.
 HA2G_API int ha2g_pack_dims(int rows, int K, int* rows_p, int* chunks_p) {
-    *rows_p = round_up(rows, 128);
+    *rows_p = round_up(rows, 256);  // 256: the widest N tile reads 256 rows of the B operand
     *chunks_p = round_up(round_up(K, 8) / 8, PBK / 8);
     return 0;
 }
@@ -314,15 +336,28 @@ HA2G_API int ha2g_gemm_packed(const void* a_hi, const void* a_lo, int rows_pa, c
     if (M <= 0 || N <= 0) return 0;
     if (split_k > 1 && act != 0) return (int)cudaErrorInvalidValue;
     if (terms == 3) {
+        if (N >= 384) return launch_packed<256, 3>(a_hi, a_lo, rows_pa, b_hi, b_lo, rows_pb, C, bias, M, N, chunks_p, ldc, act, accumulate, split_k, stream);
         if (N > 64) return launch_packed<128, 3>(a_hi, a_lo, rows_pa, b_hi, b_lo, rows_pb, C, bias, M, N, chunks_p, ldc, act, accumulate, split_k, stream);
         return launch_packed<64, 3>(a_hi, a_lo, rows_pa, b_hi, b_lo, rows_pb, C, bias, M, N, chunks_p, ldc, act, accumulate, split_k, stream);
     }
+    if (N >= 384) return launch_packed<256, 1>(a_hi, a_lo, rows_pa, b_hi, b_lo, rows_pb, C, bias, M, N, chunks_p, ldc, act, accumulate, split_k, stream);
     if (N > 64) return launch_packed<128, 1>(a_hi, a_lo, rows_pa, b_hi, b_lo, rows_pb, C, bias, M, N, chunks_p, ldc, act, accumulate, split_k, stream);
     return launch_packed<64, 1>(a_hi, a_lo, rows_pa, b_hi, b_lo, rows_pb, C, bias, M, N, chunks_p, ldc, act, accumulate, split_k, stream);
 }
 
-// Drop-in with the ha2g_gemm contract: packs both operands into a stream-ordered scratch allocation, runs the packed
-// GEMM, frees the scratch on the stream.  (terms: 3 = fp32-accurate, 1 = bf16.)
+// Scratch arena for the packing passes: the host registers ONE device buffer (torch-allocated) per process; calls on the
+// same stream reuse it safely (stream order).  Without a (large enough) arena the call falls back to a stream-ordered
+// cudaMallocAsync/cudaFreeAsync pair (~60 us of allocator latency per call, measured).
+static unsigned char* g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+HA2G_API int ha2g_set_workspace(void* ptr, int64_t bytes) {
+    g_ws = reinterpret_cast<unsigned char*>(ptr);
+    g_ws_bytes = ptr != nullptr ? (size_t)bytes : 0;
+    return 0;
+}
+
+// Drop-in with the ha2g_gemm contract: packs both operands into the scratch arena, runs the packed GEMM.
+// (terms: 3 = fp32-accurate, 1 = bf16.)
 HA2G_API int ha2g_gemm_tc2(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
                            int ldb, int ldc, int transA, int transB, int act, int accumulate, int split_k, int kseg_len,
                            int kseg_stride, int terms, cudaStream_t stream) {
@@ -331,14 +366,39 @@ HA2G_API int ha2g_gemm_tc2(const float* A, const float* B, float* C, const float
     ha2g_pack_dims(M, K, &rpa, &cp);
     ha2g_pack_dims(N, K, &rpb, &cp2);
     const size_t a_bytes = (size_t)rpa * cp * 16, b_bytes = (size_t)rpb * cp * 16;
-    unsigned char* ws = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * (a_bytes + b_bytes), stream);
-    if (e != cudaSuccess) return (int)e;
+    const size_t need = 2 * (a_bytes + b_bytes);
+    unsigned char* ws = g_ws;
+    const bool own = (ws == nullptr || need > g_ws_bytes);
+    if (own) {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), need, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     unsigned char *ah = ws, *al = ws + a_bytes, *bh = ws + 2 * a_bytes, *bl = ws + 2 * a_bytes + b_bytes;
+    // skinny outputs with a long reduction (e.g. the 4032->32 head projections): too few output tiles to fill 148 SMs,
+    // so split K automatically (needs a zero-initialised C and no activation)
+    if (split_k <= 1 && act == 0) {
+        const int bn = N >= 384 ? 256 : (N > 64 ? 128 : 64);
+        const int tiles = ha2g_div_up(N, bn) * ha2g_div_up(M, PBM);
+        const int stages = cp / (PBK / 8);
+        if (tiles * 2 <= 148 && stages >= 16) {
+            int s = 148 / tiles;
+            if (s > 8) s = 8;
+            if (s > stages / 4) s = stages / 4;
+            if (s > 1) {
+                if (!accumulate) {
+                    cudaError_t em = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
+                    if (em != cudaSuccess) return (int)em;
+                }
+                split_k = s;
+            }
+        }
+    }
     int rc = ha2g_pack_bf16x2(A, lda, M, K, transA ? 0 : 1, kseg_len, kseg_stride, ah, al, stream);
     if (rc == 0) rc = ha2g_pack_bf16x2(B, ldb, N, K, transB ? 1 : 0, kseg_len, kseg_stride, bh, bl, stream);
     if (rc == 0) rc = ha2g_gemm_packed(ah, al, rpa, bh, bl, rpb, C, bias, M, N, cp, ldc, act, accumulate, split_k, terms, stream);
-    cudaError_t e2 = cudaFreeAsync(ws, stream);
-    if (rc != 0) return rc;
-    return (int)e2;
+    if (own) {
+        cudaError_t e2 = cudaFreeAsync(ws, stream);
+        if (rc == 0) rc = (int)e2;
+    }
+    return rc;
 }

@@ -6,6 +6,7 @@ CPU tensors or a missing library raise.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -45,7 +46,21 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 _prof = {"on": False, "only": None, "flops_fn": None, "recs": {}}
 
 
+_workspace = {}
+
+
+def _ensure_workspace():
+    """One torch-allocated scratch arena per device for the operand-packing passes of the tensor-core GEMMs."""
+    dev = torch.cuda.current_device()
+    if dev not in _workspace:
+        _workspace[dev] = torch.empty(int(os.environ.get("HA2G_WORKSPACE_MB", "512")) << 20, dtype=torch.uint8, device=f"cuda:{dev}")
+        lib.ha2g_set_workspace(_workspace[dev].data_ptr(), _workspace[dev].numel())
+    return _workspace[dev]
+
+
 def _call(name: str, *args):
+    if not _workspace:
+        _ensure_workspace()
     LAUNCHES[0] += 1
     if _prof["on"] and (_prof["only"] is None or _prof["only"] == name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -36,3 +36,33 @@ for impl in ("f32", "tc", "tc2"):
             ts.append(e0.elapsed_time(e1))
         t = sorted(ts)[len(ts) // 2]
         print(f"{impl:4s} {M:5d}x{N:4d}x{K:5d} tA={tA} tB={tB} split={split}: {t * 1e3:8.1f} us  {2.0 * M * N * K / t / 1e9:8.2f} TFLOP/s  ({note})")
+
+# packed GEMM alone (operands already packed): isolates the tensor-core main loop from the packing passes
+import ctypes
+from ha2g_b200._lib import lib
+from ha2g_b200.ops import _p, _st
+for (M, N, K, note) in [(4352, 900, 600, "gi projection"), (900, 600, 4352, "dW_ih shape"), (4352, 300, 600, "TCN")]:
+    rp = ctypes.c_int(); cp = ctypes.c_int(); rpb = ctypes.c_int(); cpb = ctypes.c_int()
+    A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); C = torch.zeros(M, N, device=dev)
+    lib.ha2g_pack_dims(M, K, ctypes.addressof(rp), ctypes.addressof(cp))
+    lib.ha2g_pack_dims(N, K, ctypes.addressof(rpb), ctypes.addressof(cpb))
+    ah = torch.empty(rp.value * cp.value * 16, dtype=torch.uint8, device=dev); al = torch.empty_like(ah)
+    bh = torch.empty(rpb.value * cp.value * 16, dtype=torch.uint8, device=dev); bl = torch.empty_like(bh)
+    lib.ha2g_pack_bf16x2(_p(A), K, M, K, 1, 0, 0, _p(ah), _p(al), _st())
+    lib.ha2g_pack_bf16x2(_p(B), K, N, K, 1, 0, 0, _p(bh), _p(bl), _st())
+    for terms in (3, 1):
+        for split in (1, 4):
+            ts = []
+            for it in range(6):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                lib.ha2g_gemm_packed(_p(ah), _p(al), rp.value, _p(bh), _p(bl), rpb.value, _p(C), None, M, N, cp.value, N, 0, 0, split, terms, _st())
+                e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+            t = sorted(ts)[len(ts) // 2]
+            print(f"packed-only terms={terms} split={split} {M}x{N}x{K}: {t * 1e3:7.1f} us  {2.0 * M * N * K / t / 1e9:8.2f} TFLOP/s fp32-equiv ({note})")
+    ts = []
+    for it in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); lib.ha2g_pack_bf16x2(_p(A), K, M, K, 1, 0, 0, _p(ah), _p(al), _st()); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    print(f"pack A {M}x{K}: {sorted(ts)[1] * 1e3:.1f} us")
