@@ -4,7 +4,47 @@ from __future__ import annotations
 
 import torch
 
+import ctypes
+import os
+
+from ._lib import lib
 from .ops import _c, _call, _chk, _p, _st
+
+_CONV_IMPL = os.environ.get("HA2G_CONV_IMPL", "tc")  # "tc": tcgen05 for stride-1 fwd/dgrad; "f32": SIMT everywhere
+# operand split on the tensor cores: tf32x3 (default; ~2^-21 product error, needed by the ill-conditioned train-mode-BN
+# encoder gradients) or bf16x3 (2^-16; half the tensor time and operand bytes)
+_CONV_PREC = 0 if os.environ.get("HA2G_CONV_PRECISION", "tf32x3") == "bf16x3" else 1
+
+
+def set_conv_precision(mode: str):
+    global _CONV_PREC
+    _CONV_PREC = 0 if mode == "bf16x3" else 1
+
+
+def set_conv_impl(impl: str):
+    global _CONV_IMPL
+    _CONV_IMPL = impl
+
+
+def _tc_ok(Cs, Cd, stride):
+    return _CONV_IMPL == "tc" and stride == 1 and Cs % (4 if _CONV_PREC else 8) == 0 and Cd % 4 == 0
+
+
+def _conv_tc(src, w, bias, N, H, W, Cs, Cd, pad, KH, KW, dgrad):
+    """Stride-1 correlation of the NHWC tensor `src` [N,H,W,Cs] with the OIHW weight `w` on tcgen05 (csrc/conv_tc.cu)."""
+    dev = src.device
+    guard, rows_p, chunks_p = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib.ha2g_conv_tc_dims(N, H, W, Cs, pad, KH, KW, _CONV_PREC, ctypes.addressof(guard), ctypes.addressof(rows_p), ctypes.addressof(chunks_p))
+    a = torch.empty((2, rows_p.value * chunks_p.value * 16), dtype=torch.uint8, device=dev)
+    _call("ha2g_conv_tc_pack_act", _p(src), N, H, W, Cs, pad, KH, KW, _CONV_PREC, _p(a[0]), _p(a[1]), _st())
+    Cout, Cin = w.shape[0], w.shape[1]
+    rows_pb = (Cd + 255) // 256 * 256
+    b = torch.empty((2, rows_pb * KH * KW * chunks_p.value * 16), dtype=torch.uint8, device=dev)
+    _call("ha2g_conv_tc_pack_w", _p(w), Cout, Cin, KH, KW, int(dgrad), _CONV_PREC, _p(b[0]), _p(b[1]), _st())
+    Ho, Wo = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
+    out = torch.empty((N, Ho, Wo, Cd), device=dev, dtype=torch.float32)
+    _call("ha2g_conv_tc", _p(a[0]), _p(a[1]), _p(b[0]), _p(b[1]), _p(bias), _p(out), N, H, W, Cs, Cd, pad, KH, KW, _CONV_PREC, _st())
+    return out
 
 
 class _Conv2dFn(torch.autograd.Function):
@@ -18,6 +58,11 @@ class _Conv2dFn(torch.autograd.Function):
         Cout, _, KH, KW = w.shape
         Ho = (H + 2 * pad - KH) // stride + 1
         Wo = (W + 2 * pad - KW) // stride + 1
+        ctx.cfg = (N, H, W, Cin, Cout, KH, KW, stride, pad)
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, w)
+        if _tc_ok(Cin, Cout, stride):
+            return _conv_tc(x, w, b, N, H, W, Cin, Cout, pad, KH, KW, False)
         wf = torch.empty((KH * KW * Cin, Cout), device=x.device, dtype=torch.float32)
         _call("ha2g_conv2d_pack", _p(w), _p(wf), Cout, Cin, KH, KW, 0, _st())
         y = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
@@ -34,7 +79,10 @@ class _Conv2dFn(torch.autograd.Function):
         dy = _c(dy)
         dev = dy.device
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and _tc_ok(Cout, Cin, stride):
+            Ho, Wo = dy.shape[1], dy.shape[2]
+            dx = _conv_tc(dy, w, None, N, Ho, Wo, Cout, Cin, KH - 1 - pad, KH, KW, True)
+        elif ctx.needs_input_grad[0]:
             wb = torch.empty((KH * KW * Cout, Cin), device=dev, dtype=torch.float32)
             _call("ha2g_conv2d_pack", _p(w), _p(wb), Cout, Cin, KH, KW, 1, _st())
             dx = torch.empty((N, H, W, Cin), device=dev, dtype=torch.float32)
