@@ -418,3 +418,97 @@ HA2G_API int ha2g_conv_tc(const void* a_hi, const void* a_lo, const void* b_hi, 
 #undef CONV_LAUNCH
     HA2G_RETURN_LAST();
 }
+
+// ---- weight gradient on the packed tensor-core GEMM ------------------------------------------------------------------
+// dwf[(r*KW+s)*Cin + ci][co] = sum_p x[p shifted by tap (r,s)][ci] * dy[p][co]   (stride 1).
+// The reduction runs over output pixels, so both GEMM operands are "K-leading"; they are packed block-wise over the pixel
+// range (blocks sized to stay L2-resident between the packing pass and the GEMM): an im2col-gather writes the x operand
+// [rows = KH*KW*Cin][K = pixels] directly in the packed bf16 hi/lo layout, dy is packed by ha2g_pack_bf16x2, and
+// ha2g_gemm_packed (gemm_tc2.cu) accumulates each block into dwf with split-K.
+extern "C" int ha2g_pack_bf16x2(const float*, int, int, int, int, int, int, void*, void*, cudaStream_t);
+extern "C" int ha2g_gemm_packed(const void*, const void*, int, const void*, const void*, int, float*, const float*, int, int,
+                                int, int, int, int, int, int, cudaStream_t);
+extern "C" int ha2g_pack_dims(int, int, int*, int*);
+
+namespace {
+__global__ void im2col_pack_kernel(const float* __restrict__ x, int N, int H, int W, int Cin, int KH, int KW, int pad, int Ho,
+                                   int Wo, int64_t p_begin, int p_valid, int rows, int rows_p, int chunks_p,
+                                   uint4* __restrict__ hi, uint4* __restrict__ lo) {
+    const int64_t total = (int64_t)rows_p * chunks_p;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e % rows_p);
+        const int c = (int)(e / rows_p);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (row < rows) {
+            const int tap = row / Cin, ci = row % Cin;
+            const int r = tap / KW - pad, s = tap % KW - pad;
+            // decode the first pixel of the chunk once (32-bit: N*Ho*Wo < 2^31), then walk (wo, ho, n) with carries
+            const int pl0 = c * 8;
+            const int p0 = (int)p_begin + pl0;
+            int wo = p0 % Wo, t1 = p0 / Wo;
+            int ho = t1 % Ho, n = t1 / Ho;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (pl0 + i < p_valid) {
+                    const int ih = ho + r, iw = wo + s;
+                    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v[i] = x[(((size_t)n * H + ih) * W + iw) * Cin + ci];
+                }
+                if (++wo == Wo) { wo = 0; if (++ho == Ho) { ho = 0; ++n; } }
+            }
+        }
+        uint4 h4, l4;
+        make_chunk<false>(v, h4, l4);
+        hi[e] = h4;
+        lo[e] = l4;
+    }
+}
+}  // namespace
+
+// workspace bytes for ha2g_conv_wgrad_tc (one pixel block of both packed operands)
+HA2G_API int ha2g_conv_wgrad_tc_workspace(int Cin, int Cout, int KH, int KW, int64_t* bytes, int* block_pixels) {
+    const int rows_pa = cround(KH * KW * Cin, 128), rows_pb = cround(Cout, 256);
+    int64_t px = ((int64_t)48 << 20) / ((int64_t)rows_pa * 4);   // packed x-operand block <= 48 MB (hi + lo)
+    px = px / 32 * 32;
+    if (px < 1024) px = 1024;
+    if (px > (1 << 20)) px = 1 << 20;
+    *block_pixels = (int)px;
+    *bytes = (int64_t)(rows_pa + rows_pb) * (px / 8) * 32;
+    return 0;
+}
+
+// dwf [KH*KW*Cin, Cout] += weight gradient of a stride-1 convolution (x [N,H,W,Cin], dy [N,Ho,Wo,Cout], NHWC fp32)
+HA2G_API int ha2g_conv_wgrad_tc(const float* x, const float* dy, float* dwf, int N, int H, int W, int Cin, int Cout, int KH,
+                                int KW, int pad, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+    const int Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
+    const int64_t P = (int64_t)N * Ho * Wo;
+    const int rows = KH * KW * Cin;
+    const int rows_pa = cround(rows, 128), rows_pb = cround(Cout, 256);
+    int64_t need; int block_px;
+    ha2g_conv_wgrad_tc_workspace(Cin, Cout, KH, KW, &need, &block_px);
+    if (workspace == nullptr || workspace_bytes < need) return (int)cudaErrorInvalidValue;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    const size_t a_plane = (size_t)rows_pa * (block_px / 8) * 16, b_plane = (size_t)rows_pb * (block_px / 8) * 16;
+    unsigned char *ah = ws, *al = ws + a_plane, *bh = ws + 2 * a_plane, *bl = ws + 2 * a_plane + b_plane;
+    const int bn = Cout >= 384 ? 256 : (Cout > 64 ? 128 : 64);
+    const int tiles = ha2g_div_up(Cout, bn) * ha2g_div_up(rows, 128);
+    for (int64_t p0 = 0; p0 < P; p0 += block_px) {
+        const int pv = (int)((P - p0) < block_px ? (P - p0) : block_px);
+        int rp_unused, chunks_p;
+        ha2g_pack_dims(Cout, pv, &rp_unused, &chunks_p);   // chunks_p = pixels/8 rounded up to a multiple of 4
+        const int64_t total = (int64_t)rows_pa * chunks_p;
+        im2col_pack_kernel<<<ha2g_ew_grid(total, 256, 2), 256, 0, stream>>>(x, N, H, W, Cin, KH, KW, pad, Ho, Wo, p0, pv, rows,
+                                                                           rows_pa, chunks_p, reinterpret_cast<uint4*>(ah),
+                                                                           reinterpret_cast<uint4*>(al));
+        int rc = ha2g_pack_bf16x2(dy + p0 * Cout, Cout, Cout, pv, 0, 0, 0, bh, bl, stream);
+        if (rc != 0) return rc;
+        const int stages = chunks_p / 4;
+        int split = ha2g_div_up(296, tiles);
+        if (split > stages / 4) split = stages / 4;
+        if (split < 1) split = 1;
+        rc = ha2g_gemm_packed(ah, al, rows_pa, bh, bl, rows_pb, dwf, nullptr, rows, Cout, chunks_p, Cout, 0, 1, split, 3, stream);
+        if (rc != 0) return rc;
+    }
+    HA2G_RETURN_LAST();
+}

@@ -16,6 +16,9 @@ _CONV_IMPL = os.environ.get("HA2G_CONV_IMPL", "tc")  # "tc": tcgen05 for stride-
 _CONV_PREC = 0 if os.environ.get("HA2G_CONV_PRECISION", "tf32x3") == "bf16x3" else 1
 
 
+_WGRAD_TC = os.environ.get("HA2G_WGRAD_IMPL", "tc") == "tc"  # weight gradient on the packed tcgen05 GEMM (bf16x3)
+
+
 def set_conv_precision(mode: str):
     global _CONV_PREC
     _CONV_PREC = 0 if mode == "bf16x3" else 1
@@ -89,7 +92,13 @@ class _Conv2dFn(torch.autograd.Function):
             _call("ha2g_conv2d_dgrad", _p(dy), _p(wb), _p(dx), N, H, W, Cin, Cout, KH, KW, stride, pad, _st())
         if ctx.needs_input_grad[1]:
             dwf = torch.zeros((KH * KW * Cin, Cout), device=dev, dtype=torch.float32)
-            _call("ha2g_conv2d_wgrad", _p(x), _p(dy), _p(dwf), N, H, W, Cin, Cout, KH, KW, stride, pad, _st())
+            if _CONV_IMPL == "tc" and stride == 1 and _WGRAD_TC and Cin >= 64:  # Cin <= 32: the 9x im2col blow-up costs more than SIMT
+                nbytes, blk = ctypes.c_int64(), ctypes.c_int()
+                lib.ha2g_conv_wgrad_tc_workspace(Cin, Cout, KH, KW, ctypes.addressof(nbytes), ctypes.addressof(blk))
+                ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)
+                _call("ha2g_conv_wgrad_tc", _p(x), _p(dy), _p(dwf), N, H, W, Cin, Cout, KH, KW, pad, _p(ws), nbytes.value, _st())
+            else:
+                _call("ha2g_conv2d_wgrad", _p(x), _p(dy), _p(dwf), N, H, W, Cin, Cout, KH, KW, stride, pad, _st())
             dw = torch.empty_like(w)
             _call("ha2g_conv2d_pack", _p(dwf), _p(dw), Cout, Cin, KH, KW, 2, _st())
         if ctx.has_bias and ctx.needs_input_grad[2]:
