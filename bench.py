@@ -246,25 +246,38 @@ def main():
             ms = float(t.item())
         return ms, ret
 
-    # warm-up (also selects the dominant launcher: one step with every launcher timed by CUDA events)
-    for i in range(max(a.warmup - 1, 2)):
+    from ha2g_b200 import graph_step
+    # set-up: the public step runs eagerly twice, then captures itself into one CUDA graph (graph_step.py); these
+    # calls are outside the warm-up count so that every warm-up and timed step below is the steady-state path
+    for i in range(graph_step.WARMUP + 1 if graph_step.enabled() else 1):
         step(i, False)
-    ops.profile_begin(all_launchers=True, flops_fn=launcher_flops)
-    step(0, False)
-    prof = ops.profile_end()
-    top = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
+    for i in range(max(a.warmup, 3)):
+        step(i, False)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     n0 = ops.LAUNCHES[0]
-    ops.profile_begin(only=top, flops_fn=launcher_flops)
     ms, ret = timed(a.steps, False)
-    topstat = ops.profile_end().get(top, None)
     launches = (ops.LAUNCHES[0] - n0)
     ms_e2e, ret = timed(a.steps, True)
     clocks = sampler.stop() if rank == 0 else None
+
+    # roofline leg: the same step launcher by launcher (eager, CUDA events around every C-ABI call on the launching
+    # stream): one pass picks the dominant launcher, `steps` more passes time only that one
+    ops.profile_begin(all_launchers=True, flops_fn=launcher_flops)
+    step(0, False)
+    prof = ops.profile_end()
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
+    ops.profile_begin(only=top, flops_fn=launcher_flops)
+    barrier()
+    for i in range(a.steps):
+        step(i, False)
+    barrier()
+    topstat = ops.profile_end().get(top, None)
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     frames = a.batch * T_FRAMES * world
@@ -280,16 +293,19 @@ def main():
         achieved = topstat["flops"] / (topstat["ms"] * 1e-3) / 1e12 if topstat["ms"] > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                    "calls_in_timed_region": topstat["calls"], "ms_in_timed_region": topstat["ms"],
+                    "calls_timed": topstat["calls"], "ms_timed": topstat["ms"],
                     "share_of_step": topstat["ms"] / ms if ms > 0 else None,
-                    "note": "achieved = algorithmic FLOPs of the launcher's calls / CUDA-event time of those calls inside the "
-                            "timed region; fp32 SIMT parity path measured against the bf16 tensor peak"}
+                    "note": "achieved = algorithmic FLOPs of the launcher's calls / CUDA-event time of those calls over "
+                            f"{a.steps} eager passes of the same step right after the timed region (the timed region itself "
+                            "replays one CUDA graph, which has no per-kernel host events); fp32-accurate bf16x3 path "
+                            "measured against the dense bf16 tensor peak"}
     line = {"metric": metric, "value": frames * a.steps / (ms * 1e-3), "unit": "pose-frames/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": frames * a.steps / (ms_e2e * 1e-3), "unit": "pose-frames/s",
                     "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * (len(ret) + len(gens) + 2) * world},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "gpu_launches": launches, "cuda_graph": {"enabled": graph_step.enabled(), **graph_step.STATS},
+            "clocks": clocks, "roofline": roofline,
             "step_tflops": step_flops(a.variant, a.batch * world) * a.steps / (ms * 1e-3) / 1e12,
             "last_losses": {k: round(v, 5) for k, v in ret.items()},
             "profile_top5": sorted(((k, round(v["ms"], 3), v["calls"]) for k, v in prof.items()), key=lambda r: -r[1])[:5]}

@@ -30,6 +30,38 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const int64_t* __restri
         p[i] -= step_size * (mi / denom);
     }
 }
+// CUDA-graph variant: the step count and the hyper-parameters live in device memory, so one captured launch stays
+// valid for every replay.  state[0] = step count (incremented here); hyper = {lr, b1, b2, eps}; the bias corrections
+// are written to hyper[4..5] for the update kernel that follows on the same stream.
+__global__ void adam_tick_kernel(int* __restrict__ step, double* __restrict__ hyper) {
+    const int s = ++(*step);
+    hyper[4] = 1.0 - pow(hyper[1], (double)s);
+    hyper[5] = sqrt(1.0 - pow(hyper[2], (double)s));
+}
+__global__ void __launch_bounds__(256) adam_multi_dev_kernel(const int64_t* __restrict__ table, const int64_t* __restrict__ sizes,
+                                                             const int* __restrict__ chunk_tensor,
+                                                             const int64_t* __restrict__ chunk_off,
+                                                             const double* __restrict__ hyper) {
+    const float lr = (float)hyper[0], b1 = (float)hyper[1], b2 = (float)hyper[2], eps = (float)hyper[3];
+    const float bc1 = (float)hyper[4], bc2_sqrt = (float)hyper[5];
+    const int k = chunk_tensor[blockIdx.x];
+    const int64_t off = chunk_off[blockIdx.x];
+    float* __restrict__ p = reinterpret_cast<float*>(table[4 * k + 0]);
+    const float* __restrict__ g = reinterpret_cast<const float*>(table[4 * k + 1]);
+    float* __restrict__ m = reinterpret_cast<float*>(table[4 * k + 2]);
+    float* __restrict__ v = reinterpret_cast<float*>(table[4 * k + 3]);
+    const int64_t n = sizes[k];
+    const int64_t end = min(n, off + ADAM_CHUNK);
+    const float step_size = lr / bc1;
+    for (int64_t i = off + threadIdx.x; i < end; i += blockDim.x) {
+        float gi = g[i];
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= step_size * (mi / denom);
+    }
+}
 }  // namespace
 
 // table: [ntensors*4] int64 device addresses (p,g,m,v), sizes: [ntensors] int64, chunk maps built by the host
@@ -41,5 +73,16 @@ HA2G_API int ha2g_adam_multi(const int64_t* table, const int64_t* sizes, const i
     const double bc2 = 1.0 - pow((double)b2, (double)step);
     adam_multi_kernel<<<nchunks, 256, 0, stream>>>(table, sizes, chunk_tensor, chunk_off, lr, b1, b2, eps, (float)bc1,
                                                    (float)sqrt(bc2));
+    HA2G_RETURN_LAST();
+}
+
+// Same update with the step counter (int, device, incremented by this call) and hyper = {lr, b1, b2, eps, -, -, -, -}
+// (8 doubles, device; slots 4..5 are scratch for the bias corrections) read from device memory: the launch can be
+// captured once into a CUDA graph and replayed while the host only rewrites `hyper` when a schedule changes lr.
+HA2G_API int ha2g_adam_multi_dev(const int64_t* table, const int64_t* sizes, const int* chunk_tensor,
+                                 const int64_t* chunk_off, int nchunks, double* hyper, int* step, cudaStream_t stream) {
+    if (nchunks <= 0) return 0;
+    adam_tick_kernel<<<1, 1, 0, stream>>>(step, hyper);
+    adam_multi_dev_kernel<<<nchunks, 256, 0, stream>>>(table, sizes, chunk_tensor, chunk_off, hyper);
     HA2G_RETURN_LAST();
 }

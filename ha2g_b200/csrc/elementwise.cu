@@ -363,3 +363,28 @@ HA2G_API int ha2g_unfold1d_bwd(const float* dout, float* dx, int64_t B, int T, i
 HA2G_API int ha2g_pack_conv1d_w(const float* src, float* dst, int O, int I, int Kw, int inverse, cudaStream_t stream) {
     EW_LAUNCH(pack_conv1d_w_kernel, (int64_t)O * I * Kw, src, dst, O, I, Kw, inverse);
 }
+
+namespace {
+// perm[rank(j)] = j with rank(j) = #{k : key[k] < key[j] or (key[k] == key[j] and k < j)}: a uniformly random
+// permutation when the keys are i.i.d. uniform draws.  O(n^2) compares; n is the batch size (<= a few thousand).
+__global__ void __launch_bounds__(256) rank_perm_kernel(const float* __restrict__ keys, int64_t* __restrict__ perm, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float kj = keys[j];
+    int r = 0;
+    for (int k = 0; k < n; ++k) {
+        const float kk = keys[k];
+        r += (kk < kj || (kk == kj && k < j)) ? 1 : 0;
+    }
+    perm[r] = (int64_t)j;
+}
+}  // namespace
+
+// torch.randperm(n) for the mismatched-speaker pass (scripts/train_eval/train_hierarchy_expressive.py:328) from n uniform
+// keys: stream-ordered, no host synchronisation, capturable into a CUDA graph.  Bit-exact index contract: perm is a
+// permutation of 0..n-1 (int64).
+HA2G_API int ha2g_rank_perm(const float* keys, int64_t* perm, int n, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    rank_perm_kernel<<<ha2g_div_up(n, 256), 256, 0, stream>>>(keys, perm, n);
+    HA2G_RETURN_LAST();
+}

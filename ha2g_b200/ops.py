@@ -95,15 +95,29 @@ def gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, tA=0, tB=0, act=0, acc=0, split=
     _call("ha2g_gemm", _p(A), _p(B), _p(C), _p(bias), M, N, K, lda, ldb, ldc, tA, tB, act, acc, split, _st())
 
 
+_config = {"gemm_impl": "auto", "precision": "fp32x3"}
+
+
 def set_gemm_impl(impl: str):
     """'auto' (default): packed tcgen05 bf16x3 GEMM for problems big enough to amortise packing, exact fp32 SIMT for
     the small ones; 'f32': SIMT only; 'tc': register-staged tcgen05 kernel everywhere; 'tc2': packed kernel everywhere."""
     lib.ha2g_set_gemm_impl({"f32": 0, "auto": 1, "tc": 2, "tc2": 3}[impl])
+    _config["gemm_impl"] = impl
 
 
 def set_precision(mode: str):
     """'fp32x3' (default): three-term bf16 split, fp32-accurate; 'bf16': plain bf16 operands on the tensor cores."""
     lib.ha2g_set_gemm_terms(1 if mode == "bf16" else 3)
+    _config["precision"] = mode
+
+
+def config_signature() -> tuple:
+    """Kernel-selection switches that get baked into a captured CUDA graph (graph_step keys its cache on them)."""
+    return (_config["gemm_impl"], _config["precision"], os.environ.get("HA2G_GRU_IMPL", ""))
+
+
+def profiling() -> bool:
+    return bool(_prof["on"])
 
 
 def col_sum_into(x2d: torch.Tensor, out: torch.Tensor):

@@ -82,3 +82,96 @@ def fused_adam_step(optimizer: torch.optim.Optimizer):
         b1, b2 = group["betas"]
         _call("ha2g_adam_multi", _p(c["table"]), _p(c["sizes_t"]), _p(c["ct"]), _p(c["co"]), c["n"], float(group["lr"]),
               float(b1), float(b2), float(group["eps"]), step, _st())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CUDA-graph variant: step count and hyper-parameters in device memory (csrc/adam.cu::ha2g_adam_multi_dev)
+# ----------------------------------------------------------------------------------------------------------------
+def _hyper_of(group):
+    b1, b2 = group["betas"]
+    return (float(group["lr"]), float(b1), float(b2), float(group["eps"]))
+
+
+def graph_prepare(optimizer: torch.optim.Optimizer):
+    """Outside capture, after at least one eager step (moments exist, the set of parameters that receive a gradient is
+    known): allocate the per-group device tables the captured Adam launch will read."""
+    entries = []
+    for group in optimizer.param_groups:
+        if group.get("amsgrad", False) or group.get("weight_decay", 0) != 0 or group.get("maximize", False):
+            raise NotImplementedError("fused_adam_step covers the reference's configuration (plain Adam)")
+        params = [p for p in group["params"] if p.grad is not None]
+        if not params:
+            entries.append(None)
+            continue
+        dev = params[0].device
+        sizes = [p.numel() for p in params]
+        ct, co = [], []
+        for k, n in enumerate(sizes):
+            for off in range(0, n, CHUNK):
+                ct.append(k)
+                co.append(off)
+        steps = {int(optimizer.state[p]["step"]) for p in params}
+        if len(steps) != 1:
+            raise NotImplementedError("parameters of one group must share the Adam step count")
+        step0 = steps.pop()
+        hh = _hyper_of(group)
+        entries.append({
+            "params": params, "n": len(ct),
+            "sizes_t": torch.tensor(sizes, dtype=torch.int64, device=dev),
+            "ct": torch.tensor(ct, dtype=torch.int32, device=dev),
+            "co": torch.tensor(co, dtype=torch.int64, device=dev),
+            "table": torch.zeros((4 * len(params),), dtype=torch.int64, device=dev),
+            "hyper": torch.tensor(list(hh) + [0.0] * 4, dtype=torch.float64, device=dev), "hyper_host": hh,
+            "step": torch.tensor([step0], dtype=torch.int32, device=dev), "step_host": step0,
+            "rows": None, "grads": None})
+    return entries
+
+
+@torch.no_grad()
+def graph_adam_enqueue(optimizer: torch.optim.Optimizer, entries):
+    """Inside capture: record the (p, g, m, v) addresses (uploaded by graph_finalize once capture has ended) and
+    enqueue the device-hyper Adam launch."""
+    for group, e in zip(optimizer.param_groups, entries):
+        params = [p for p in group["params"] if p.grad is not None]
+        if e is None:
+            if params:
+                raise RuntimeError("a parameter group without gradients in the warm-up steps received one during capture")
+            continue
+        if len(params) != len(e["params"]) or any(a is not b for a, b in zip(params, e["params"])):
+            raise RuntimeError("the set of parameters receiving gradients changed between warm-up and capture")
+        rows = []
+        for p in params:
+            st = optimizer.state[p]
+            if not p.grad.is_contiguous() or not p.is_contiguous():
+                raise RuntimeError("fused Adam needs contiguous parameters and gradients")
+            rows += [p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()]
+        e["rows"], e["grads"] = rows, [p.grad for p in params]
+        _call("ha2g_adam_multi_dev", _p(e["table"]), _p(e["sizes_t"]), _p(e["ct"]), _p(e["co"]), e["n"], _p(e["hyper"]),
+              _p(e["step"]), _st())
+
+
+def graph_finalize(entries):
+    """After capture: upload the address tables recorded during capture."""
+    for e in entries:
+        if e is not None:
+            e["table"].copy_(torch.tensor(e["rows"], dtype=torch.int64))
+
+
+def graph_pre_replay(optimizer: torch.optim.Optimizer, entries):
+    """Host side of one replay: keep torch's own optimizer state (``step``) and the device copies of the
+    hyper-parameters in agreement, and point ``p.grad`` at the graph's static gradient buffers."""
+    for group, e in zip(optimizer.param_groups, entries):
+        if e is None:
+            continue
+        hh = _hyper_of(group)
+        if hh != e["hyper_host"]:  # e.g. an lr schedule: rare, a small synchronous upload
+            e["hyper"][:4].copy_(torch.tensor(hh, dtype=torch.float64))
+            e["hyper_host"] = hh
+        params = e["params"]
+        s = int(optimizer.state[params[0]]["step"])
+        if s != e["step_host"]:   # an eager step ran in between
+            e["step"].fill_(s)
+        for p, g in zip(params, e["grads"]):
+            optimizer.state[p]["step"] += 1
+            p.grad = g
+        e["step_host"] = s + 1

@@ -15,7 +15,7 @@ from typing import Callable, List, Optional
 
 import torch
 
-_state = {"dropout": True, "randn": None, "mask": None, "randperm": None}
+_state = {"dropout": True, "randn": None, "mask": None, "randperm": None, "graph_safe": False}
 
 
 def dropout_enabled() -> bool:
@@ -38,12 +38,24 @@ def dropout_mask(shape, p: float, device) -> torch.Tensor:
 def randperm(n: int, device) -> torch.Tensor:
     if _state["randperm"] is not None:
         return _state["randperm"](n).to(device)
-    return torch.randperm(n, device=device)
+    # rank of n uniform keys (csrc/elementwise.cu::rank_perm_kernel): stream-ordered and CUDA-graph capturable,
+    # which torch.randperm's host-side checks are not
+    from .ops import _call, _p, _st
+    keys = torch.rand((n,), device=device, dtype=torch.float32)
+    perm = torch.empty((n,), device=device, dtype=torch.int64)
+    _call("ha2g_rank_perm", _p(keys), _p(perm), n, _st())
+    return perm
 
 
 @contextlib.contextmanager
+def overridden() -> bool:
+    """True while any draw is injected (tests): such steps must not be captured into a replayable CUDA graph, unless
+    the injected sources are stateless device-side functions (``override(graph_safe=True)``)."""
+    return (not _state["graph_safe"]) and any(_state[k] is not None for k in ("randn", "mask", "randperm"))
+
+
 def override(randn_fn: Optional[Callable] = None, mask_fn: Optional[Callable] = None,
-             randperm_fn: Optional[Callable] = None, dropout: Optional[bool] = None):
+             randperm_fn: Optional[Callable] = None, dropout: Optional[bool] = None, graph_safe: bool = False):
     """Inject deterministic draws (tests) or switch dropout off (parity with the no-dropout goldens)."""
     old = dict(_state)
     if randn_fn is not None:
@@ -54,6 +66,7 @@ def override(randn_fn: Optional[Callable] = None, mask_fn: Optional[Callable] = 
         _state["randperm"] = randperm_fn
     if dropout is not None:
         _state["dropout"] = dropout
+    _state["graph_safe"] = bool(graph_safe)
     try:
         yield
     finally:

@@ -11,7 +11,11 @@ mechanical and result-preserving:
     computes then discards those gradients: dis_optimizer.zero_grad() precedes the next use);
   * loss terms are back-propagated as several roots with constant weights instead of being summed into
     one scalar first (identical gradients, no scalar arithmetic kernels);
-  * all ``.item()`` reads are packed into a single device->host copy at the end of the step.
+  * all ``.item()`` reads are packed into a single device->host copy at the end of the step;
+  * after two eager calls per (modules, shapes, mode) signature the whole step -- forward, both backwards, the
+    gradient all-reduce and the eight Adam updates, ~7 600 kernel launches -- is captured into ONE CUDA graph
+    (``ha2g_b200/graph_step.py``) and every later call is: copy the four inputs into the graph's static buffers,
+    replay, read the packed scalars.  ``HA2G_CUDA_GRAPH=0`` keeps the eager path.
 """
 from __future__ import annotations
 
@@ -20,7 +24,7 @@ from typing import Dict, List
 
 import torch
 
-from .. import cascade, dp, ops_loss, rng
+from .. import cascade, dp, graph_step, ops_loss, rng
 from ..optim import fused_adam_step, zero_grad
 
 
@@ -43,6 +47,23 @@ def _w(value: float, like: torch.Tensor) -> torch.Tensor:
 def train_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_indices, gens: List, discriminator,
                audio_encoder, text_encoder, gen_optimizers: List, dis_optimizer, audio_optimizer, text_optimizer
                ) -> Dict[str, float]:
+    """The drop-in step: CUDA-graph replay when a captured graph exists for this signature, eager otherwise."""
+    world = (variant, args, epoch, in_text_padded, in_spec, target, vid_indices, gens, discriminator, audio_encoder,
+             text_encoder, gen_optimizers, dis_optimizer, audio_optimizer, text_optimizer)
+    hit = graph_step.run(enqueue_step, world)
+    if hit is not None:
+        names, vals, flags = hit
+    else:
+        names, packed, flags = enqueue_step(*world)
+        vals = packed.tolist()
+    return _finish(args, names, vals, flags)
+
+
+def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_indices, gens: List, discriminator,
+                 audio_encoder, text_encoder, gen_optimizers: List, dis_optimizer, audio_optimizer, text_optimizer,
+                 adam=fused_adam_step):
+    """Enqueue one whole step on the current stream without any host synchronisation.
+    -> (names, packed device tensor of the step's scalars, flags for _finish)."""
     warm_up_epochs = args.loss_warmup
     n_pre = args.n_pre_poses
     dev = target.device
@@ -66,7 +87,7 @@ def train_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_i
         one = _w(1.0, target)
         torch.autograd.backward([l_real, l_fake], [one, one])
         dp.allreduce_grads(dis_optimizer)
-        fused_adam_step(dis_optimizer)
+        adam(dis_optimizer)
         scalars["dis_real"], scalars["dis_fake"] = l_real.detach(), l_fake.detach()
 
     # ------------------------------------------------------------------ train G
@@ -121,13 +142,19 @@ def train_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_i
 
     for opt in list(gen_optimizers) + [audio_optimizer, text_optimizer]:
         dp.allreduce_grads(opt)   # no-op on one GPU
-        fused_adam_step(opt)
+        adam(opt)
 
     # ------------------------------------------------------------------ one packed device->host read
     names = list(scalars.keys())
-    vals = torch.cat([scalars[n].reshape(1) for n in names]).tolist()
+    packed = torch.cat([scalars[n].reshape(1) for n in names])
+    return names, packed, {"use_reg": use_reg, "gan_on": gan_on, "levels": len(outs)}
+
+
+def _finish(args, names, vals, flags) -> Dict[str, float]:
+    """The reference's returned dict of python floats (train_hierarchy_expressive.py:468-483)."""
+    use_reg, gan_on = flags["use_reg"], flags["gan_on"]
     v = dict(zip(names, vals))
-    huber_loss = sum(v[f"huber{k}"] for k in range(len(outs)))
+    huber_loss = sum(v[f"huber{k}"] for k in range(flags["levels"]))
     ret_dict = {"loss": args.loss_regression_weight * huber_loss}
     if use_reg:
         if v["kld"]:

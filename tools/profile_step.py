@@ -19,7 +19,8 @@ def main():
     a = ap.parse_args()
     import torch
     import bench
-    from ha2g_b200 import ops
+    from ha2g_b200 import graph_step, ops
+    graph_step.enable(False)   # the same launches, issued one by one: ncu then lists every kernel under its own name
     from ha2g_b200.synthetic import make_batch
     from ha2g_b200.train_eval.train_hierarchy import train_iter_hierarchy
     from ha2g_b200.train_eval.train_hierarchy_expressive import train_iter_hierarchy_expressive
