@@ -20,6 +20,18 @@ static inline int ha2g_ew_grid(int64_t n, int threads = 256, int per_thread = 4)
     return (int)(want < cap ? want : cap);
 }
 
+// Exactly one lane of a CONVERGED warp.  tcgen05.mma / cp.async.bulk are uniform-datapath instructions: guarded by
+// elect.sync (with warp-uniform operands) they issue directly from uniform registers; guarded by `lane == 0` the
+// compiler wraps every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~145 cycles per instruction,
+// measured on the GRU recurrence: 4 170 -> ~600 cycles for 60 MMAs).
+__device__ __forceinline__ bool ha2g_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// threadIdx.x / 32 as a provably warp-uniform value (so that role branches are uniform branches)
+__device__ __forceinline__ int ha2g_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ float ha2g_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(CNT) conv_tc_kernel(const uint4* __restrict__ 
     uint64_t* bar_done = bar_wempty + CWST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = ha2g_warp_id(), lane = tid & 31;
     const int q0 = g.guard + blockIdx.y * CBM;          // first padded output position (packed row index) of this tile
     const int n0 = blockIdx.x * BN;
     const int taps = g.KH * g.KW;
@@ -215,10 +215,10 @@ __global__ void __launch_bounds__(CNT) conv_tc_kernel(const uint4* __restrict__ 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (ha2g_elect_one()) {
             int wit = 0;
             for (int ab = 0; ab < n_ablk; ++ab) {
                 if (ab > 0) cmb_wait(bar_aempty, (ab - 1) & 1);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(CNT) conv_tc_kernel(const uint4* __restrict__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (ha2g_elect_one()) {
             const uint32_t fmt = TF32 ? 2u : 1u;  // instruction-descriptor A/B format: 1 = BF16, 2 = TF32
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CBM >> 4) << 24);
             const uint32_t lbo_a = (uint32_t)(g.RA * 16);

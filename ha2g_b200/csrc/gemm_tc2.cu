@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
     uint64_t* bar_done = bar_empty + PST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = ha2g_warp_id(), lane = tid & 31;
     const int m0 = blockIdx.y * PBM, n0 = blockIdx.x * BN;
     const int total_stages = chunks_p / (PBK / 8);
     const int sb = blockIdx.z * stages_per_split;
@@ -157,11 +157,11 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ===== producer: one thread streams packed chunks with 1-D bulk copies =====
-        if (lane == 0) {
+        if (ha2g_elect_one()) {
             constexpr uint32_t bytes = (uint32_t)((TERMS == 3 ? 2 : 1) * (S::A_BYTES + S::B_BYTES));
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % PST;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (ha2g_elect_one()) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PBM >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % PST;

@@ -32,9 +32,14 @@ extern "C" int ha2g_gru_seq_bwd_cluster(const float*, int, int, const float*, co
 extern "C" int ha2g_gru_tc_supported(int H, int* ok);
 extern "C" int ha2g_gru_seq_fwd_tc(const float*, const float*, const float*, const float*, const float*, float*, float*, int,
                                    int, int, cudaStream_t);
+extern "C" int ha2g_gru_tc2_supported(int H, int* ok);
+extern "C" int ha2g_gru_seq_fwd_tc2(const float*, const float*, const float*, const float*, const float*, float*, float*, int,
+                                    int, int, cudaStream_t);
 // HA2G_GRU_IMPL = step    : per-step kernels of this file
 //               = cluster : persistent cluster kernels, fp32 FMA inner product (gru_cluster.cu)
-//               = (unset) : persistent cluster kernels with the tcgen05 forward recurrence (gru_cluster_tc.cu)
+//               = tc      : tcgen05 forward recurrence, W_hh slice in shared memory (gru_cluster_tc.cu)
+//               = (unset) : tcgen05 forward recurrence, W_hh slice in tensor memory, bulk-copy h exchange
+//                           (gru_cluster_tc2.cu)
 static bool use_cluster_path(int H) {
     const char* e = getenv("HA2G_GRU_IMPL");
     if (e != nullptr && strcmp(e, "step") == 0) return false;
@@ -47,6 +52,14 @@ static bool use_tc_recurrence(int H) {
     if (e != nullptr && (strcmp(e, "step") == 0 || strcmp(e, "cluster") == 0)) return false;
     int ok = 0;
     ha2g_gru_tc_supported(H, &ok);
+    return ok != 0;
+}
+
+static bool use_tc2_recurrence(int H) {
+    const char* e = getenv("HA2G_GRU_IMPL");
+    if (e != nullptr && e[0] != 0) return false;
+    int ok = 0;
+    ha2g_gru_tc2_supported(H, &ok);
     return ok != 0;
 }
 
@@ -189,6 +202,7 @@ HA2G_API int ha2g_gru_layer_fwd(const float* x, int I, const float* w_ih_f, cons
     const int MT = M * T;
     HA2G_CHECK(ha2g_gemm(x, w_ih_f, gi, b_ih_f, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
     HA2G_CHECK(ha2g_gemm(x, w_ih_r, gi + 3 * H, b_ih_r, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
+    if (use_tc2_recurrence(H)) return ha2g_gru_seq_fwd_tc2(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, stream);
     if (use_tc_recurrence(H)) return ha2g_gru_seq_fwd_tc(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, stream);
     if (use_cluster_path(H)) return ha2g_gru_seq_fwd_cluster(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, stream);
     dim3 grid(ha2g_div_up(H, GR_HID), ha2g_div_up(M, GR_ROWS), 2);

@@ -47,13 +47,13 @@ def randperm(n: int, device) -> torch.Tensor:
     return perm
 
 
-@contextlib.contextmanager
 def overridden() -> bool:
     """True while any draw is injected (tests): such steps must not be captured into a replayable CUDA graph, unless
     the injected sources are stateless device-side functions (``override(graph_safe=True)``)."""
     return (not _state["graph_safe"]) and any(_state[k] is not None for k in ("randn", "mask", "randperm"))
 
 
+@contextlib.contextmanager
 def override(randn_fn: Optional[Callable] = None, mask_fn: Optional[Callable] = None,
              randperm_fn: Optional[Callable] = None, dropout: Optional[bool] = None, graph_safe: bool = False):
     """Inject deterministic draws (tests) or switch dropout off (parity with the no-dropout goldens)."""

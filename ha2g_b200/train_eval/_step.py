@@ -61,9 +61,11 @@ def train_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_i
 
 def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_indices, gens: List, discriminator,
                  audio_encoder, text_encoder, gen_optimizers: List, dis_optimizer, audio_optimizer, text_optimizer,
-                 adam=fused_adam_step):
+                 adam=None):
     """Enqueue one whole step on the current stream without any host synchronisation.
     -> (names, packed device tensor of the step's scalars, flags for _finish)."""
+    if adam is None:
+        adam = fused_adam_step   # resolved at call time (the eager multi-tensor step; graph capture passes its own)
     warm_up_epochs = args.loss_warmup
     n_pre = args.n_pre_poses
     dev = target.device

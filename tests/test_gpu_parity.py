@@ -87,7 +87,8 @@ def test_gemm_variants(impl, tol):
 def test_gru_layer_vs_torch():
     """ha2g_gru_layer_fwd/bwd against torch.nn.GRU (CPU) for H=300 (generator) and H=64 (discriminator)."""
     from ha2g_b200 import ops
-    for (M, T, I, H, L) in [(3, 34, 105, 300, 2), (5, 28, 8, 64, 4), (33, 7, 20, 16, 1)]:
+    for (M, T, I, H, L) in [(3, 34, 105, 300, 2), (5, 28, 8, 64, 4), (33, 7, 20, 16, 1), (133, 9, 24, 300, 1), (2, 1, 8, 64, 1),
+                            (2, 2, 8, 64, 2)]:
         torch.manual_seed(1)
         gru = torch.nn.GRU(I, H, L, batch_first=True, bidirectional=True)
         x = torch.randn(M, T, I, requires_grad=True)

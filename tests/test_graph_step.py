@@ -1,5 +1,11 @@
 """The whole-step CUDA graph (ha2g_b200/graph_step.py) must be indistinguishable from the eager step:
-same losses, same parameters after N steps, torch's optimizer state kept in agreement, lr changes honoured."""
+same losses, same parameter updates, torch's optimizer state kept in agreement, lr changes honoured.
+
+Trajectories of this step are chaotic at tiny batch (Adam's first updates are lr*sign(g); two EAGER runs from the
+same state differ by 1e-5 / 1e-4 / 4e-3 in the losses of steps 1 / 2 / 3, `tools/determinism_check.py`), so the
+sharp comparison is a single step from a synchronised state; whole trajectories are only held to a growing bound."""
+import copy
+
 import pytest
 import torch
 
@@ -10,74 +16,142 @@ from ha2g_b200.synthetic import make_batch
 pytestmark = pytest.mark.gpu
 
 SEEDS = {"gens": 20, "dis": 30, "audio": 31, "text": 32}
+DEV = "cuda:0"
 
 
-def _world(variant, dev):
-    args, gens, D, A, T = build_modules(variant, 60, 5, SEEDS, dev)
-    lr = args.learning_rate
-    mk = lambda m, l=lr: torch.optim.Adam(m.parameters(), lr=l, betas=(0.5, 0.999))
-    opts = [mk(g) for g in gens] + [mk(D, lr * args.discriminator_lr_weight), mk(A), mk(T)]
-    return args, gens, D, A, T, opts
+class World:
+    def __init__(self, variant, B=4):
+        from ha2g_b200.train_eval.train_hierarchy import train_iter_hierarchy
+        from ha2g_b200.train_eval.train_hierarchy_expressive import train_iter_hierarchy_expressive
+        self.variant, self.B = variant, B
+        self.fn = train_iter_hierarchy if variant == "gesture" else train_iter_hierarchy_expressive
+        self.args, self.gens, self.D, self.A, self.T = build_modules(variant, 60, 5, SEEDS, DEV)
+        lr = self.args.learning_rate
+        mk = lambda m, l=lr: torch.optim.Adam(m.parameters(), lr=l, betas=(0.5, 0.999))
+        self.opts = [mk(g) for g in self.gens] + [mk(self.D, lr * self.args.discriminator_lr_weight), mk(self.A), mk(self.T)]
+        g = torch.Generator().manual_seed(3)
+        # 3 cascade passes x L generators draw reparameterisation noise each step: a fixed cycle of distinct draws
+        # (the same in every step and in every world; stateless, hence safe to bake into a graph)
+        self.noise = [torch.randn((B, 16), generator=g).to(DEV) for _ in range(3 * len(self.gens))]
+        self.perm = torch.randperm(B, generator=g).to(DEV)
+        self.calls = 0
+
+    @property
+    def mods(self):
+        return self.gens + [self.D, self.A, self.T]
+
+    def _randn(self, shape):
+        self.calls += 1
+        return self.noise[(self.calls - 1) % len(self.noise)]
+
+    def step(self, i):
+        b = {k: v.to(DEV) for k, v in make_batch(self.variant, self.B, 60, 5, seed=500 + i).items()}
+        with rng.override(randn_fn=self._randn, randperm_fn=lambda n: self.perm, dropout=False, graph_safe=True):
+            return self.fn(self.args, 11, b["in_text_padded"], b["in_spec"], b["target"], b["vid"], *self.mods, *self.opts)
+
+    def params(self):
+        return [p.detach().clone() for m in self.mods for p in m.parameters()]
+
+    def steps(self):
+        return {int(o.state[p]["step"]) for o in self.opts for grp in o.param_groups for p in grp["params"] if p in o.state}
+
+    def load_from(self, other):
+        for m, mo in zip(self.mods, other.mods):
+            m.load_state_dict(copy.deepcopy(mo.state_dict()))
+        for o, oo in zip(self.opts, other.opts):
+            o.load_state_dict(copy.deepcopy(oo.state_dict()))
+        self.calls = other.calls
 
 
-def _run(variant, graph_on, n_steps, B=4, lr_zero_at=None):
-    from ha2g_b200.train_eval.train_hierarchy import train_iter_hierarchy
-    from ha2g_b200.train_eval.train_hierarchy_expressive import train_iter_hierarchy_expressive
-    dev = "cuda:0"
-    fn = train_iter_hierarchy if variant == "gesture" else train_iter_hierarchy_expressive
-    args, gens, D, A, T, opts = _world(variant, dev)
-    g = torch.Generator().manual_seed(3)
-    noise = torch.randn((B, 16), generator=g).to(dev)
-    perm = torch.randperm(B, generator=g).to(dev)
+@pytest.fixture(autouse=True)
+def _fresh_graph_cache():
     graph_step.reset()
-    graph_step.enable(graph_on)
-    rets, snaps = [], []
-    try:
-        # stateless device-side draws: identical in every step of both runs, and safe to bake into a graph
-        with rng.override(randn_fn=lambda shape: noise, randperm_fn=lambda n: perm, dropout=False, graph_safe=True):
-            for i in range(n_steps):
-                if lr_zero_at is not None and i == lr_zero_at:
-                    for o in opts:
-                        for grp in o.param_groups:
-                            grp["lr"] = 0.0
-                b = {k: v.to(dev) for k, v in make_batch(variant, B, 60, 5, seed=500 + i).items()}
-                rets.append(fn(args, 11, b["in_text_padded"], b["in_spec"], b["target"], b["vid"], *gens, D, A, T, *opts))
-                snaps.append([p.detach().clone() for m in gens + [D, A, T] for p in m.parameters()])
-        torch.cuda.synchronize()
-        stats = dict(graph_step.STATS)
-    finally:
-        graph_step.enable(True)
-        graph_step.reset()
-    params = {f"m{mi}.{n}": p.detach().clone() for mi, m in enumerate(gens + [D, A, T]) for n, p in m.named_parameters()}
-    steps = [int(o.state[p]["step"]) for o in opts for grp in o.param_groups for p in grp["params"] if p in o.state]
-    return rets, params, steps, stats, snaps
+    graph_step.enable(True)
+    yield
+    graph_step.enable(True)
+    graph_step.reset()
+
+
+def _close_losses(a, b, tol, what):
+    assert set(a) == set(b), what
+    for k in a:
+        assert abs(a[k] - b[k]) <= tol * max(1.0, abs(a[k])), (what, k, a[k], b[k])
 
 
 @pytest.mark.parametrize("variant", ["gesture", "expressive"])
 def test_graph_matches_eager(variant):
-    n = 5
+    n = 4
     s0 = dict(graph_step.STATS)
-    e_rets, e_params, e_steps, _, _ = _run(variant, False, n)
-    g_rets, g_params, g_steps, stats, _ = _run(variant, True, n)
-    assert stats["captures"] - s0["captures"] == 1 and stats["replays"] - s0["replays"] == n - graph_step.WARMUP
-    for i, (a, b) in enumerate(zip(e_rets, g_rets)):
-        assert set(a) == set(b)
-        for k in a:
-            assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (i, k, a[k], b[k])
-    assert e_steps == g_steps and set(g_steps) == {n}
+    wg = World(variant)
+    g_rets = [wg.step(i) for i in range(n)]
+    assert graph_step.STATS["captures"] - s0["captures"] == 1
+    assert graph_step.STATS["replays"] - s0["replays"] == n - graph_step.WARMUP
+    assert wg.steps() == {n}
+
+    # (1) sharp: one more step from a synchronised state, graph replay vs eager
+    graph_step.enable(False)
+    we = World(variant)
+    we.load_from(wg)
+    before = we.params()
+    r_e = we.step(n)
+    graph_step.enable(True)
+    r_g = wg.step(n)
+    assert graph_step.STATS["replays"] - s0["replays"] == n - graph_step.WARMUP + 1
+    _close_losses(r_e, r_g, 1e-3, "synchronised step")
+    assert wg.steps() == {n + 1} and we.steps() == {n + 1}
     lr = 5e-4
-    for k in e_params:
-        d = (e_params[k] - g_params[k]).abs()
-        # identical kernels in identical order; only atomics ordering differs, which Adam's sign-like first steps can
-        # turn into isolated +-lr flips
-        assert float(d.max()) <= 2.2 * lr * n, (k, float(d.max()))
-        assert float((d > 0.05 * lr).float().mean()) <= 0.02, (k, float((d > 0.05 * lr).float().mean()))
+    bad = tot = 0
+    for k, (p0, pe, pg) in enumerate(zip(before, we.params(), wg.params())):
+        d = (pe - pg).abs()
+        assert float(d.max()) <= 2.2 * lr, (k, float(d.max()))   # at worst an Adam sign flip of a noise-level gradient
+        bad += int((d > 0.05 * lr).sum())
+        tot += d.numel()
+    # elements whose update differs by more than 5% of one lr step: only where the gradient is fp32 noise (e.g. the
+    # 8..16-element SE biases of the train-mode-BatchNorm audio encoder, see tests/helpers.py), a tiny share overall
+    assert bad <= 0.005 * tot, (bad, tot)
+    assert any(not torch.equal(p0, pg) for p0, pg in zip(before, wg.params()))
+
+    # (2) loose: the whole trajectory against an all-eager run (bound grows with the chaos of the trajectory)
+    graph_step.enable(False)
+    w2 = World(variant)
+    e_rets = [w2.step(i) for i in range(n)]
+    for i, (a, b) in enumerate(zip(e_rets, g_rets)):
+        _close_losses(a, b, 3e-3 * 10 ** max(0, i - 2), f"trajectory step {i}")
 
 
 def test_graph_honours_lr_change():
     # lr -> 0 before the 4th call (a replay): parameters must stop moving, losses must keep being computed
-    rets, _, steps, stats, snaps = _run("gesture", True, 4, lr_zero_at=3)
+    w = World("gesture")
+    snaps, rets = [], []
+    for i in range(4):
+        if i == 3:
+            for o in w.opts:
+                for grp in o.param_groups:
+                    grp["lr"] = 0.0
+        rets.append(w.step(i))
+        snaps.append(w.params())
+    assert graph_step.STATS["replays"] >= 2
     assert any(not torch.equal(a, b) for a, b in zip(snaps[1], snaps[2]))   # the first replay (lr > 0) moved them
     for a, b in zip(snaps[2], snaps[3]):
         assert torch.equal(a, b)
-    assert set(steps) == {4} and all(v == v for v in rets[3].values())
+    assert w.steps() == {4} and all(v == v for v in rets[3].values())
+
+
+def test_graph_and_eager_interleave():
+    # an eager step between replays (e.g. an injected-randomness step) must not desynchronise the device-side Adam
+    # step counter or leave p.grad pointing at stale buffers
+    w = World("gesture")
+    for i in range(3):
+        w.step(i)
+    graph_step.enable(False)
+    w.step(3)
+    graph_step.enable(True)
+    r = w.step(4)
+    assert w.steps() == {5} and all(v == v for v in r.values())
+    we = World("gesture")
+    graph_step.enable(False)
+    we.load_from(w)
+    r_e = we.step(5)
+    graph_step.enable(True)
+    r_g = w.step(5)
+    _close_losses(r_e, r_g, 1e-3, "after interleaving")
