@@ -55,6 +55,19 @@ static bool use_tc_recurrence(int H) {
     return ok != 0;
 }
 
+extern "C" int ha2g_gru_tc2_bwd_supported(int H, int* ok);
+extern "C" int ha2g_gru_seq_bwd_tc2(const float*, int, int, const float*, const float*, const float*, const float*, float*,
+                                    float*, int, int, int, cudaStream_t);
+// backward recurrence on tcgen05 (gru_cluster_tc2_bwd.cu) unless HA2G_GRU_IMPL / HA2G_GRU_BWD_IMPL select an older path
+static bool use_tc2_bwd(int H) {
+    const char* e = getenv("HA2G_GRU_IMPL");
+    if (e != nullptr && e[0] != 0) return false;
+    const char* b = getenv("HA2G_GRU_BWD_IMPL");
+    if (b != nullptr && strcmp(b, "cluster") == 0) return false;
+    int ok = 0;
+    ha2g_gru_tc2_bwd_supported(H, &ok);
+    return ok != 0;
+}
 static bool use_tc2_recurrence(int H) {
     const char* e = getenv("HA2G_GRU_IMPL");
     if (e != nullptr && e[0] != 0) return false;
@@ -227,8 +240,11 @@ HA2G_API int ha2g_gru_layer_bwd(const float* dy, int dy_ld, int dy_dir_stride, c
     cudaError_t ce = cudaMemsetAsync(dh_rec, 0, sizeof(float) * (size_t)M * 2 * H, stream);
     if (ce != cudaSuccess) return (int)ce;
     const int ew_grid = ha2g_ew_grid((int64_t)M * 2 * H, 256, 1);
-    const bool clustered = use_cluster_path(H);
-    if (clustered)
+    const bool tc2 = use_tc2_bwd(H);
+    const bool clustered = tc2 || use_cluster_path(H);
+    if (tc2)
+        HA2G_CHECK(ha2g_gru_seq_bwd_tc2(dy, dy_ld, dy_dir_stride, y, gates, w_hh_f, w_hh_r, dgi, dgh, M, T, H, stream));
+    else if (clustered)
         HA2G_CHECK(ha2g_gru_seq_bwd_cluster(dy, dy_ld, dy_dir_stride, y, gates, w_hh_f, w_hh_r, dgi, dgh, M, T, H, stream));
     for (int s = T - 1; s >= 0 && !clustered; --s) {
         gru_gates_bwd_kernel<<<ew_grid, 256, 0, stream>>>(dy, dy_ld, dy_dir_stride, y, gates, dgi, dgh, dh_rec, M, T, H, s);

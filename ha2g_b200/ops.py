@@ -113,7 +113,8 @@ def set_precision(mode: str):
 
 def config_signature() -> tuple:
     """Kernel-selection switches that get baked into a captured CUDA graph (graph_step keys its cache on them)."""
-    return (_config["gemm_impl"], _config["precision"], os.environ.get("HA2G_GRU_IMPL", ""))
+    return (_config["gemm_impl"], _config["precision"], os.environ.get("HA2G_GRU_IMPL", ""),
+            os.environ.get("HA2G_GRU_BWD_IMPL", ""))
 
 
 def profiling() -> bool:

@@ -116,7 +116,7 @@ def test_graph_matches_eager(variant):
     w2 = World(variant)
     e_rets = [w2.step(i) for i in range(n)]
     for i, (a, b) in enumerate(zip(e_rets, g_rets)):
-        _close_losses(a, b, 3e-3 * 10 ** max(0, i - 2), f"trajectory step {i}")
+        _close_losses(a, b, 3e-3 if i < 2 else 1e-2 * 10 ** (i - 2), f"trajectory step {i}")
 
 
 def test_graph_honours_lr_change():

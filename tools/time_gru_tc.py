@@ -45,3 +45,28 @@ for impl in ("cluster",):
     e1.record(); torch.cuda.synchronize()
     print(f"max |y_tc2 - y_fp32cluster| = {float((yref - y).abs().max()):.3e} (|y| max {float(y.abs().max()):.3f})")
     print(f"fp32 cluster kernel: {e0.elapsed_time(e1) * 1e3:.1f} us total, {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
+
+# ---- backward recurrence: tcgen05 kernel vs the fp32 cluster kernel ------------------------------------------------
+dy = torch.randn(M, T, 2 * H, device=dev) * 0.1
+lib.ha2g_gru_seq_fwd_tc2(_p(gi), _p(w[0]), _p(w[1]), _p(b[0]), _p(b[1]), _p(y), _p(gates), M, T, H, _st())
+dgi = torch.empty(M, T, 6 * H, device=dev); dgh = torch.empty_like(dgi)
+dgi2 = torch.empty_like(dgi); dgh2 = torch.empty_like(dgi)
+for _ in range(3):
+    lib.ha2g_gru_seq_bwd_tc2_dbg(_p(dy), 2 * H, H, _p(y), _p(gates), _p(w[0]), _p(w[1]), _p(dgi), _p(dgh), M, T, H, _p(dbg), _st())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+lib.ha2g_gru_seq_bwd_tc2_dbg(_p(dy), 2 * H, H, _p(y), _p(gates), _p(w[0]), _p(w[1]), _p(dgi), _p(dgh), M, T, H, _p(dbg), _st())
+e1.record(); torch.cuda.synchronize()
+dall = dbg.view(T + 1, 8).cpu(); d = dall[:T]; pr = dall[T]
+print(f"bwd tc2: kernel {e0.elapsed_time(e1) * 1e3:.1f} us total, {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
+for i, nme in enumerate(["wait for partials", "reduce + gate grads + B operand", "MMA (72) + dgi/dgh copy-out", "TMEM->staging->bulk copies"]):
+    print(f"   {nme:34s}: {(d[5:T - 1, i + 1] - d[5:T - 1, i]).float().mean():8.0f} cycles")
+print(f"   round period                      : {(d[6:T - 1, 0] - d[5:T - 2, 0]).float().mean():8.0f} cycles")
+print(f"   prologue: W->smem {int(pr[1] - pr[0])}, smem->TMEM {int(pr[2] - pr[1])}, to loop start {int(pr[3] - pr[2])}; loop {int(pr[4] - pr[3])} cycles")
+for _ in range(2):
+    lib.ha2g_gru_seq_bwd_cluster(_p(dy), 2 * H, H, _p(y), _p(gates), _p(w[0]), _p(w[1]), _p(dgi2), _p(dgh2), M, T, H, _st())
+e0.record()
+lib.ha2g_gru_seq_bwd_cluster(_p(dy), 2 * H, H, _p(y), _p(gates), _p(w[0]), _p(w[1]), _p(dgi2), _p(dgh2), M, T, H, _st())
+e1.record(); torch.cuda.synchronize()
+print(f"bwd fp32 cluster kernel: {e0.elapsed_time(e1) * 1e3:.1f} us total;  max|dgi diff| {float((dgi - dgi2).abs().max()):.3e} (max {float(dgi2.abs().max()):.3e}), "
+      f"max|dgh diff| {float((dgh - dgh2).abs().max()):.3e}")
