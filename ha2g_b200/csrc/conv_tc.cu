@@ -425,7 +425,7 @@ HA2G_API int ha2g_conv_tc(const void* a_hi, const void* a_lo, const void* b_hi, 
 // range (blocks sized to stay L2-resident between the packing pass and the GEMM): an im2col-gather writes the x operand
 // [rows = KH*KW*Cin][K = pixels] directly in the packed bf16 hi/lo layout, dy is packed by ha2g_pack_bf16x2, and
 // ha2g_gemm_packed (gemm_tc2.cu) accumulates each block into dwf with split-K.
-extern "C" int ha2g_pack_bf16x2(const float*, int, int, int, int, int, int, void*, void*, cudaStream_t);
+extern "C" int ha2g_pack_bf16x2_rows(const float*, int, int, int, int, int, int, int, void*, void*, cudaStream_t);
 extern "C" int ha2g_gemm_packed(const void*, const void*, int, const void*, const void*, int, float*, const float*, int, int,
                                 int, int, int, int, int, int, cudaStream_t);
 extern "C" int ha2g_pack_dims(int, int, int*, int*);
@@ -466,9 +466,11 @@ __global__ void im2col_pack_kernel(const float* __restrict__ x, int N, int H, in
 }
 }  // namespace
 
+static inline int wgrad_bn(int Cout) { return Cout >= 384 ? 256 : (Cout > 64 ? 128 : 64); }   // N tile of ha2g_gemm_packed
+
 // workspace bytes for ha2g_conv_wgrad_tc (one pixel block of both packed operands)
 HA2G_API int ha2g_conv_wgrad_tc_workspace(int Cin, int Cout, int KH, int KW, int64_t* bytes, int* block_pixels) {
-    const int rows_pa = cround(KH * KW * Cin, 128), rows_pb = cround(Cout, 256);
+    const int rows_pa = cround(KH * KW * Cin, 128), rows_pb = cround(Cout, wgrad_bn(Cout));
     int64_t px = ((int64_t)48 << 20) / ((int64_t)rows_pa * 4);   // packed x-operand block <= 48 MB (hi + lo)
     px = px / 32 * 32;
     if (px < 1024) px = 1024;
@@ -484,14 +486,14 @@ HA2G_API int ha2g_conv_wgrad_tc(const float* x, const float* dy, float* dwf, int
     const int Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
     const int64_t P = (int64_t)N * Ho * Wo;
     const int rows = KH * KW * Cin;
-    const int rows_pa = cround(rows, 128), rows_pb = cround(Cout, 256);
+    const int rows_pa = cround(rows, 128), rows_pb = cround(Cout, wgrad_bn(Cout));
     int64_t need; int block_px;
     ha2g_conv_wgrad_tc_workspace(Cin, Cout, KH, KW, &need, &block_px);
     if (workspace == nullptr || workspace_bytes < need) return (int)cudaErrorInvalidValue;
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     const size_t a_plane = (size_t)rows_pa * (block_px / 8) * 16, b_plane = (size_t)rows_pb * (block_px / 8) * 16;
     unsigned char *ah = ws, *al = ws + a_plane, *bh = ws + 2 * a_plane, *bl = ws + 2 * a_plane + b_plane;
-    const int bn = Cout >= 384 ? 256 : (Cout > 64 ? 128 : 64);
+    const int bn = wgrad_bn(Cout);
     const int tiles = ha2g_div_up(Cout, bn) * ha2g_div_up(rows, 128);
     for (int64_t p0 = 0; p0 < P; p0 += block_px) {
         const int pv = (int)((P - p0) < block_px ? (P - p0) : block_px);
@@ -501,7 +503,7 @@ HA2G_API int ha2g_conv_wgrad_tc(const float* x, const float* dy, float* dwf, int
         im2col_pack_kernel<<<ha2g_ew_grid(total, 256, 2), 256, 0, stream>>>(x, N, H, W, Cin, KH, KW, pad, Ho, Wo, p0, pv, rows,
                                                                            rows_pa, chunks_p, reinterpret_cast<uint4*>(ah),
                                                                            reinterpret_cast<uint4*>(al));
-        int rc = ha2g_pack_bf16x2(dy + p0 * Cout, Cout, Cout, pv, 0, 0, 0, bh, bl, stream);
+        int rc = ha2g_pack_bf16x2_rows(dy + p0 * Cout, Cout, Cout, pv, 0, 0, 0, rows_pb, bh, bl, stream);
         if (rc != 0) return rc;
         const int stages = chunks_p / 4;
         int split = ha2g_div_up(296, tiles);

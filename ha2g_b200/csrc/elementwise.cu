@@ -388,3 +388,63 @@ HA2G_API int ha2g_rank_perm(const float* keys, int64_t* perm, int n, cudaStream_
     rank_perm_kernel<<<ha2g_div_up(n, 256), 256, 0, stream>>>(keys, perm, n);
     HA2G_RETURN_LAST();
 }
+
+namespace {
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so a dropout mask is a pure function of
+// (seed, step, call id, element index) and the backward pass regenerates it instead of reading a stored mask.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// state = {seed, step}: one step counter tick per training step makes every (step, call, element) triple unique
+__global__ void rng_tick_kernel(unsigned long long* state) { state[1] += 1ull; }
+
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n,
+                                                      uint32_t threshold, float scale,
+                                                      const unsigned long long* __restrict__ state, uint32_t call_id) {
+    const unsigned long long seed = state[0], step = state[1];
+    const uint32_t k0 = (uint32_t)seed ^ (uint32_t)(step * 0x9E3779B97F4A7C15ull >> 32), k1 = (uint32_t)(seed >> 32) ^ (uint32_t)step;
+    const int64_t n4 = (n + 3) >> 2;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), call_id, 0x2B992DDFu, k0, k1, r);
+        const int64_t i = q << 2;
+        if (i + 3 < n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+            const float4 v = *reinterpret_cast<const float4*>(x + i);
+            float4 o;
+            o.x = r[0] >= threshold ? v.x * scale : 0.f; o.y = r[1] >= threshold ? v.y * scale : 0.f;
+            o.z = r[2] >= threshold ? v.z * scale : 0.f; o.w = r[3] >= threshold ? v.w * scale : 0.f;
+            *reinterpret_cast<float4*>(y + i) = o;
+        } else {
+            for (int j = 0; j < 4 && i + j < n; ++j) y[i + j] = r[j] >= threshold ? x[i + j] * scale : 0.f;
+        }
+    }
+}
+}  // namespace
+
+// Advance the dropout stream by one training step (state = {seed, step} as two uint64 in device memory).
+HA2G_API int ha2g_rng_tick(uint64_t* state, cudaStream_t stream) {
+    rng_tick_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned long long*>(state));
+    HA2G_RETURN_LAST();
+}
+// nn.Dropout(p) forward AND backward (tcn.py:22,27, hierarchy_net.py:43,88 inter-layer GRU dropout): y = x * keep / (1-p)
+// with keep = Philox(seed, step, call_id, element) >= p * 2^32.  The backward pass calls it on the incoming gradient with
+// the same call_id: the mask is regenerated, never stored.
+HA2G_API int ha2g_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* state, uint32_t call_id,
+                          cudaStream_t stream) {
+    if (n <= 0) return 0;
+    double t = (double)p * 4294967296.0;
+    if (t < 0.0) t = 0.0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    dropout_kernel<<<ha2g_ew_grid((n + 3) / 4, 256, 2), 256, 0, stream>>>(x, y, n, (uint32_t)t, 1.f / (1.f - p),
+                                                                          reinterpret_cast<const unsigned long long*>(state), call_id);
+    HA2G_RETURN_LAST();
+}

@@ -329,6 +329,20 @@ HA2G_API int ha2g_pack_bf16x2(const float* src, int ld, int rows, int K, int kco
     HA2G_RETURN_LAST();
 }
 
+// Same packing with an explicit row padding (a multiple of the tile that will read the operand: 128 for A, the N tile --
+// 64 / 128 / 256 -- for B) instead of the conservative 256: a [32 x K] operand then writes 64 rows, not 256.
+HA2G_API int ha2g_pack_bf16x2_rows(const float* src, int ld, int rows, int K, int kcontig, int kseg_len, int kseg_stride,
+                                   int rows_p, void* hi, void* lo, cudaStream_t stream) {
+    int rp_unused, chunks_p;
+    ha2g_pack_dims(rows, K, &rp_unused, &chunks_p);
+    if (rows_p < rows || rows_p % 64 != 0) return (int)cudaErrorInvalidValue;
+    const int64_t total = (int64_t)rows_p * chunks_p;
+    pack_bf16x2_kernel<<<ha2g_ew_grid(total, 256, 2), 256, 0, stream>>>(src, ld, rows, K, kcontig, kseg_len, kseg_stride,
+                                                                        reinterpret_cast<uint4*>(hi),
+                                                                        reinterpret_cast<uint4*>(lo), rows_p, chunks_p);
+    HA2G_RETURN_LAST();
+}
+
 // C[M,N] (+)= act(A B^T + bias) on packed operands (see ha2g_pack_bf16x2); terms = 3: fp32-accurate bf16x3, 1: plain bf16.
 HA2G_API int ha2g_gemm_packed(const void* a_hi, const void* a_lo, int rows_pa, const void* b_hi, const void* b_lo,
                               int rows_pb, float* C, const float* bias, int M, int N, int chunks_p, int ldc, int act,

@@ -257,10 +257,34 @@ class _MulMaskFn(torch.autograd.Function):
         return dx, None, None
 
 
+class _DropoutFn(torch.autograd.Function):
+    """Fused Philox dropout: the mask is a function of (device seed/step, call id, element), regenerated in backward."""
+
+    @staticmethod
+    def forward(ctx, x, p, call_id):
+        x = _c(x)
+        _chk(x)
+        y = torch.empty_like(x)
+        _call("ha2g_dropout", _p(x), _p(y), x.numel(), p, _p(_rng.dropout_state(x.device)), call_id, _st())
+        ctx.cfg = (p, call_id)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, call_id = ctx.cfg
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        _call("ha2g_dropout", _p(dy), _p(dx), dy.numel(), p, _p(_rng.dropout_state(dy.device)), call_id, _st())
+        return dx, None, None
+
+
 def dropout(x, p: float, training: bool):
-    """nn.Dropout semantics; the keep-mask comes from ha2g_b200.rng (injectable for parity tests)."""
+    """nn.Dropout semantics.  Default: one fused Philox kernel per direction (no mask tensor); a test-injected mask
+    source (rng.override(mask_fn=...)) switches to explicit masks."""
     if not training or p <= 0.0 or not _rng.dropout_enabled():
         return x
+    if _rng.fused_dropout():
+        return _DropoutFn.apply(x, float(p), _rng.next_call_id())
     mask = _rng.dropout_mask(x.shape, p, x.device)
     return _MulMaskFn.apply(x, mask, 1.0 / (1.0 - p))
 
@@ -393,9 +417,13 @@ class _BiGRUFn(torch.autograd.Function):
             nxt = y
             mask = None
             if l < L - 1 and training and p > 0.0 and _rng.dropout_enabled():
-                mask = _rng.dropout_mask(y.shape, p, y.device)
                 nxt = torch.empty_like(y)
-                _call("ha2g_mul_mask", _p(y), _p(mask), 1.0 / (1.0 - p), _p(nxt), y.numel(), _st())
+                if _rng.fused_dropout():
+                    mask = _rng.next_call_id()   # the mask is regenerated from this id in backward
+                    _call("ha2g_dropout", _p(y), _p(nxt), y.numel(), float(p), _p(_rng.dropout_state(y.device)), mask, _st())
+                else:
+                    mask = _rng.dropout_mask(y.shape, p, y.device)
+                    _call("ha2g_mul_mask", _p(y), _p(mask), 1.0 / (1.0 - p), _p(nxt), y.numel(), _st())
             masks.append(mask)
             cur = nxt
         if sum_dirs:
@@ -437,7 +465,10 @@ class _BiGRUFn(torch.autograd.Function):
             grads[8 * l:8 * l + 8] = g
             if l > 0:
                 mask = ctx.masks[l - 1]
-                if mask is not None:
+                if isinstance(mask, int):
+                    dy = torch.empty_like(dx)
+                    _call("ha2g_dropout", _p(dx), _p(dy), dx.numel(), float(p), _p(_rng.dropout_state(dx.device)), mask, _st())
+                elif mask is not None:
                     dy = torch.empty_like(dx)
                     _call("ha2g_mul_mask", _p(dx), _p(mask), 1.0 / (1.0 - p), _p(dy), dx.numel(), _st())
                 else:

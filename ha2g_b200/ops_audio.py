@@ -16,6 +16,8 @@ _CONV_IMPL = os.environ.get("HA2G_CONV_IMPL", "tc")  # "tc": tcgen05 for stride-
 _CONV_PREC = 0 if os.environ.get("HA2G_CONV_PRECISION", "tf32x3") == "bf16x3" else 1
 
 
+_WGRAD_IMPLICIT = os.environ.get("HA2G_WGRAD_IMPLICIT", "1") != "0"  # tap-shifted MN-major tcgen05 kernel for "same" convolutions
+_WGRAD_TC_MIN_CIN = int(os.environ.get("HA2G_WGRAD_TC_MIN_CIN", "64"))  # below: SIMT kernel (the stem has its own)
 _WGRAD_TC = os.environ.get("HA2G_WGRAD_IMPL", "tc") == "tc"  # weight gradient on the packed tcgen05 GEMM (bf16x3)
 
 
@@ -92,7 +94,14 @@ class _Conv2dFn(torch.autograd.Function):
             _call("ha2g_conv2d_dgrad", _p(dy), _p(wb), _p(dx), N, H, W, Cin, Cout, KH, KW, stride, pad, _st())
         if ctx.needs_input_grad[1]:
             dwf = torch.zeros((KH * KW * Cin, Cout), device=dev, dtype=torch.float32)
-            if _CONV_IMPL == "tc" and stride == 1 and _WGRAD_TC and Cin >= 64:  # Cin <= 32: the 9x im2col blow-up costs more than SIMT
+            ok2, nb2 = ctypes.c_int(0), ctypes.c_int64(0)
+            if _CONV_IMPL == "tc" and stride == 1 and _WGRAD_TC and _WGRAD_IMPLICIT and dy.shape[1] == H and dy.shape[2] == W:
+                lib.ha2g_conv_wgrad_tc2_workspace(N, H, W, Cin, Cout, KH, KW, pad, ctypes.addressof(ok2), ctypes.addressof(nb2))
+            if ok2.value:
+                # implicit GEMM over the packed, zero-padded activations: no im2col (csrc/conv_wgrad_tc2.cu)
+                ws = torch.empty((nb2.value,), dtype=torch.uint8, device=dev)
+                _call("ha2g_conv_wgrad_tc2", _p(x), _p(dy), _p(dwf), N, H, W, Cin, Cout, KH, KW, pad, _p(ws), nb2.value, _st())
+            elif _CONV_IMPL == "tc" and stride == 1 and _WGRAD_TC and Cin >= _WGRAD_TC_MIN_CIN:
                 nbytes, blk = ctypes.c_int64(), ctypes.c_int()
                 lib.ha2g_conv_wgrad_tc_workspace(Cin, Cout, KH, KW, ctypes.addressof(nbytes), ctypes.addressof(blk))
                 ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)

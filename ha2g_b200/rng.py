@@ -35,6 +35,39 @@ def dropout_mask(shape, p: float, device) -> torch.Tensor:
     return (torch.rand(tuple(shape), device=device) >= p).to(torch.float32)
 
 
+# ---- fused dropout stream (csrc/elementwise.cu::dropout_kernel): Philox keyed by a device-resident {seed, step} pair ----
+_dev_state = {}
+_calls = [0]
+
+
+def dropout_state(device) -> torch.Tensor:
+    """uint64 {seed, step} in device memory (as int64); the seed is drawn once from torch's CPU generator, so
+    torch.manual_seed(...) before the first use makes runs reproducible."""
+    key = str(device)
+    if key not in _dev_state:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        _dev_state[key] = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+    return _dev_state[key]
+
+
+def next_call_id() -> int:
+    _calls[0] = (_calls[0] + 1) & 0x7FFFFFFF
+    return _calls[0]
+
+
+def begin_step(device):
+    """Once per training step (inside the captured graph too): tick the device-side step counter and restart the
+    host-side call numbering, so a replayed graph draws fresh masks with the same baked-in call ids."""
+    from .ops import _call, _p, _st
+    _call("ha2g_rng_tick", _p(dropout_state(device)), _st())
+    _calls[0] = 0
+
+
+def fused_dropout() -> bool:
+    """True when dropout masks come from the fused Philox kernel (no mask injected by a test)."""
+    return _state["mask"] is None
+
+
 def randperm(n: int, device) -> torch.Tensor:
     if _state["randperm"] is not None:
         return _state["randperm"](n).to(device)

@@ -69,6 +69,7 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
     warm_up_epochs = args.loss_warmup
     n_pre = args.n_pre_poses
     dev = target.device
+    rng.begin_step(dev)   # new dropout stream position for this step (device-side: valid under graph replay)
 
     weight, feat_low, feat_mid, feat_high, linear_blend_feat = audio_encoder(in_spec, vid_indices)
     text_feat = text_encoder(in_text_padded)

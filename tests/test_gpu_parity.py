@@ -386,3 +386,32 @@ def test_conv_tc_vs_torch(cfg):
         assert_close(bg.grad, bd.grad, f"conv {impl} dbias {cfg}", 5e-5)
     ops_audio.set_conv_impl("tc")
     ops_audio.set_conv_precision("tf32x3")
+
+
+def test_fused_dropout_kernel():
+    """ha2g_dropout: nn.Dropout semantics (keep prob 1-p, kept values scaled by 1/(1-p)), the backward pass regenerates
+    the forward mask from (seed, step, call id), different call ids / steps give independent masks."""
+    from ha2g_b200 import ops, rng
+    x = torch.ones(300, 1000, device=DEV, requires_grad=True)
+    for p in (0.1, 0.3):
+        y = ops.dropout(x, p, True)
+        keep = (y != 0)
+        assert abs(float(keep.float().mean()) - (1 - p)) < 5e-3
+        assert torch.allclose(y[keep], torch.full_like(y[keep], 1 / (1 - p)))
+        g = torch.randn_like(y)
+        (dx,) = torch.autograd.grad(y, x, g)
+        assert torch.equal(dx != 0, keep & (g != 0))                      # same mask in backward
+        assert torch.allclose(dx[keep], g[keep] / (1 - p))
+        y2 = ops.dropout(x, p, True)                                      # next call id: independent mask
+        agree = float(((y2 != 0) == keep).float().mean())
+        assert abs(agree - ((1 - p) ** 2 + p ** 2)) < 5e-3
+    # a step tick changes the stream while call ids restart
+    rng.begin_step(x.device)
+    a = ops.dropout(x, 0.3, True)
+    rng.begin_step(x.device)
+    b = ops.dropout(x, 0.3, True)
+    assert abs(float(((a != 0) == (b != 0)).float().mean()) - (0.49 + 0.09)) < 5e-3
+    assert ops.dropout(x, 0.3, False) is x
+    # ragged length (scalar tail path)
+    z = torch.ones(1001, device=DEV)
+    assert abs(float((ops.dropout(z, 0.5, True) != 0).float().mean()) - 0.5) < 0.06
