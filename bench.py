@@ -169,6 +169,19 @@ def run_cpu_port(variant, B, epoch, steps, warmup):
                       f"torch {torch.__version__} CPU, {mean_t:.2f} s/step"}, mean_t
 
 
+def _finish_process(world):
+    """Leave without tearing NCCL down: destroy_process_group() blocks for minutes while captured CUDA graphs still
+    reference the communicator (observed at N=2), and nothing after the JSON line needs a clean shutdown."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        import torch
+        from ha2g_b200 import graph_step
+        graph_step.reset()
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -276,8 +289,7 @@ def main():
     barrier()
     topstat = ops.profile_end().get(top, None)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish_process(world)
         return
 
     frames = a.batch * T_FRAMES * world
@@ -321,8 +333,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "pose-frames/s", "cores": min(os.cpu_count() or 1, 32),
                                     "kind": "port", "sample": f"failed: {type(e).__name__}"}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish_process(world)
 
 
 if __name__ == "__main__":

@@ -92,13 +92,14 @@ def split_targets(variant: str, target: torch.Tensor) -> List[torch.Tensor]:
     return [ops.gather_cols(target, t[0]) for t in tabs]
 
 
-def run_cascade(variant: str, gens, targets: List[torch.Tensor], in_text, blends, vid, n_pre: int):
-    """g1 -> ... -> gL with the pre_seq wiring; returns ([out_1..out_L], (z, mu, logvar) of the last level)."""
+def run_cascade(variant: str, gens, targets: List[torch.Tensor], in_text, blends, vid, n_pre: int, eps=None):
+    """g1 -> ... -> gL with the pre_seq wiring; returns ([out_1..out_L], (z, mu, logvar) of the last level).
+    eps: optional per-level reparameterisation noise drawn by the caller (else each generator draws its own)."""
     tabs = device_tables(variant, targets[0].device)
     outs, prev, last = [], None, None
     for k, g in enumerate(gens):
         pre = ops.pre_seq(targets[k], prev, tabs[k][1], tabs[k][2], n_pre)
-        out, z, mu, lv = g(pre, in_text, blends[k], vid)
+        out, z, mu, lv = g(pre, in_text, blends[k], vid) if eps is None else g(pre, in_text, blends[k], vid, _eps=eps[k])
         outs.append(out)
         prev, last = out, (z, mu, lv)
     return outs, last

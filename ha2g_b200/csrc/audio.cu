@@ -286,3 +286,120 @@ HA2G_API int ha2g_blend_bwd(const float* weight, const float* f0, const float* f
     blend_bwd_kernel<<<B, 256, 0, stream>>>(weight, f0, f1, f2, dweight, dblend, df0, df1, df2, dlogits, B, TC, L);
     HA2G_RETURN_LAST();
 }
+
+// ---- stride-2 convolutions as stride-1 convolutions (so that they run on the tcgen05 conv kernels) -------------------
+namespace {
+// y[n][i][j][(a*2+b)*C + c] = x[n][2i+a][2j+b][c] (0 outside);  inverse: x[n][h][w][c] = y[n][h/2][w/2][((h&1)*2+(w&1))*C + c]
+__global__ void space_to_depth2_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int C,
+                                       int H2, int W2, int inverse) {
+    const int C4 = C >> 2;
+    if (!inverse) {
+        const int64_t total = (int64_t)N * H2 * W2 * 4 * C4;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+            const int c4 = (int)(e % C4);
+            int64_t t = e / C4;
+            const int ab = (int)(t % 4); t /= 4;
+            const int j = (int)(t % W2); t /= W2;
+            const int i = (int)(t % H2);
+            const int n = (int)(t / H2);
+            const int h = 2 * i + (ab >> 1), w = 2 * j + (ab & 1);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (h < H && w < W) v = reinterpret_cast<const float4*>(src)[(((int64_t)n * H + h) * W + w) * C4 + c4];
+            reinterpret_cast<float4*>(dst)[e] = v;
+        }
+    } else {
+        const int64_t total = (int64_t)N * H * W * C4;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+            const int c4 = (int)(e % C4);
+            int64_t t = e / C4;
+            const int w = (int)(t % W); t /= W;
+            const int h = (int)(t % H);
+            const int n = (int)(t / H);
+            const int ab = ((h & 1) << 1) | (w & 1);
+            reinterpret_cast<float4*>(dst)[e] =
+                reinterpret_cast<const float4*>(src)[((((int64_t)n * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + ab) * C4 + c4];
+        }
+    }
+}
+// 3x3 stride-2 pad-1 weight w[co][c][r][s] <-> 2x2 stride-1 pad-1 weight over the space-to-depth input
+// w2[co][(a*2+b)*C + c][p][q], with r = 2p + a - 1, s = 2q + b - 1 (combinations with r or s = -1 are structural zeros).
+__global__ void conv_s2_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int C, int inverse) {
+    if (!inverse) {
+        const int64_t total = (int64_t)Cout * 4 * C * 4;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+            const int pq = (int)(e % 4);
+            int64_t t = e / 4;
+            const int c = (int)(t % C); t /= C;
+            const int ab = (int)(t % 4);
+            const int co = (int)(t / 4);
+            const int r = 2 * (pq >> 1) + (ab >> 1) - 1, s = 2 * (pq & 1) + (ab & 1) - 1;
+            dst[e] = (r >= 0 && s >= 0) ? src[(((int64_t)co * C + c) * 3 + r) * 3 + s] : 0.f;
+        }
+    } else {
+        const int64_t total = (int64_t)Cout * C * 9;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+            const int s = (int)(e % 3);
+            int64_t t = e / 3;
+            const int r = (int)(t % 3); t /= 3;
+            const int c = (int)(t % C);
+            const int co = (int)(t / C);
+            const int p = (r + 1) >> 1, a = (r + 1) & 1, q = (s + 1) >> 1, b = (s + 1) & 1;
+            dst[e] = src[((((int64_t)co * 4 + (a * 2 + b)) * C + c) * 2 + p) * 2 + q];
+        }
+    }
+}
+// y[n][i][j][:] = x[n][2i][2j][:];  inverse: x = 0 except x[n][2i][2j][:] = y[n][i][j][:]
+__global__ void subsample2_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int C, int H2,
+                                  int W2, int inverse) {
+    const int C4 = C >> 2;
+    if (!inverse) {
+        const int64_t total = (int64_t)N * H2 * W2 * C4;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+            const int c4 = (int)(e % C4);
+            int64_t t = e / C4;
+            const int j = (int)(t % W2); t /= W2;
+            const int i = (int)(t % H2);
+            const int n = (int)(t / H2);
+            reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(src)[(((int64_t)n * H + 2 * i) * W + 2 * j) * C4 + c4];
+        }
+    } else {
+        const int64_t total = (int64_t)N * H * W * C4;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+            const int c4 = (int)(e % C4);
+            int64_t t = e / C4;
+            const int w = (int)(t % W); t /= W;
+            const int h = (int)(t % H);
+            const int n = (int)(t / H);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!(h & 1) && !(w & 1)) v = reinterpret_cast<const float4*>(src)[(((int64_t)n * H2 + (h >> 1)) * W2 + (w >> 1)) * C4 + c4];
+            reinterpret_cast<float4*>(dst)[e] = v;
+        }
+    }
+}
+}  // namespace
+
+// Space-to-depth by 2 of an NHWC tensor (C % 4 == 0): [N,H,W,C] -> [N,ceil(H/2),ceil(W/2),4C] (inverse != 0: the adjoint,
+// which is the exact inverse on the un-padded positions).  With ha2g_conv_s2_weight it turns the stride-2 3x3 convolutions
+// of ResNetSE-34 (ResNetBlocks.py:12 with stride 2, ResNetSE34V2.py:97-99) into stride-1 2x2 convolutions for conv_tc.cu.
+HA2G_API int ha2g_space_to_depth2(const float* src, float* dst, int N, int H, int W, int C, int inverse, cudaStream_t stream) {
+    if (C % 4 != 0) return (int)cudaErrorInvalidValue;
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const int64_t total = inverse ? (int64_t)N * H * W * (C / 4) : (int64_t)N * H2 * W2 * C;
+    space_to_depth2_kernel<<<ha2g_ew_grid(total, 256, 2), 256, 0, stream>>>(src, dst, N, H, W, C, H2, W2, inverse);
+    HA2G_RETURN_LAST();
+}
+// w [Cout,C,3,3] -> w2 [Cout,4C,2,2] (inverse != 0: gradient of w from the gradient of w2).
+HA2G_API int ha2g_conv_s2_weight(const float* src, float* dst, int Cout, int C, int inverse, cudaStream_t stream) {
+    const int64_t total = inverse ? (int64_t)Cout * C * 9 : (int64_t)Cout * C * 16;
+    conv_s2_weight_kernel<<<ha2g_ew_grid(total, 256, 2), 256, 0, stream>>>(src, dst, Cout, C, inverse);
+    HA2G_RETURN_LAST();
+}
+// Every second pixel of an NHWC tensor (the 1x1 stride-2 downsample convolutions, ResNetSE34V2.py:70-75): [N,H,W,C] ->
+// [N,ceil(H/2),ceil(W/2),C]; inverse != 0: the adjoint (zeros at the skipped pixels).
+HA2G_API int ha2g_subsample2(const float* src, float* dst, int N, int H, int W, int C, int inverse, cudaStream_t stream) {
+    if (C % 4 != 0) return (int)cudaErrorInvalidValue;
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const int64_t total = inverse ? (int64_t)N * H * W * (C / 4) : (int64_t)N * H2 * W2 * (C / 4);
+    subsample2_kernel<<<ha2g_ew_grid(total, 256, 2), 256, 0, stream>>>(src, dst, N, H, W, C, H2, W2, inverse);
+    HA2G_RETURN_LAST();
+}

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -43,7 +44,8 @@ struct Tc2Params {
     float* y;              // [M,T,2H]
     float* gates;          // [M,T,2,4H] or nullptr
     int M, T, H, HSP, n_chunks;
-    long long* dbg;        // optional [T][8] clock64 samples of cluster 0 / rank 0 (phase timing), nullptr otherwise
+    long long* dbg;        // optional [T+1][8] clock64 samples of cluster 0 / rank 0 (phase timing), nullptr otherwise
+    int flags;             // timing experiments only (HA2G_GRU_DBGFLAGS): 1 = skip the y/gates copy-out, 2 = skip staging too
 };
 
 __device__ __forceinline__ uint32_t su32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -404,7 +406,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                 {
                     const int OR = L.orow;
                     const int narr = p.gates != nullptr ? 5 : 1;
-                    if (has_item) {
+                    if (has_item && !(p.flags & 2)) {
                         float* o = outst + (size_t)bb * OR + cc * 8;
                         reinterpret_cast<float4*>(o)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
                         reinterpret_cast<float4*>(o)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
@@ -424,7 +426,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                     // copy-out: thread -> up to two fixed (batch row, float4) positions of every line group
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        if (k < co_n) {
+                        if (k < co_n && !(p.flags & 1)) {
                             const int rb = co_rb[k], f4 = co_f4[k];
                             const int bg = m0 + rb, jg = j0 + f4 * 4;
                             if (bg < M && jg < H) {               // H % 4 == 0: a float4 is entirely valid or entirely padding
@@ -485,6 +487,7 @@ HA2G_API int ha2g_gru_seq_fwd_tc2_dbg(const float* gi, const float* w_hh_f, cons
                                       cudaStream_t stream) {
     Tc2Params p{};
     p.dbg = dbg;
+    { const char* e = dbg != nullptr ? getenv("HA2G_GRU_DBGFLAGS") : nullptr; p.flags = e != nullptr ? atoi(e) : 0; }
     p.gi = gi; p.w_hh[0] = w_hh_f; p.w_hh[1] = w_hh_r; p.b_hh[0] = b_hh_f; p.b_hh[1] = b_hh_r;
     p.y = y; p.gates = gates; p.M = M; p.T = T; p.H = H;
     p.HSP = ((H + CL - 1) / CL + 7) / 8 * 8;

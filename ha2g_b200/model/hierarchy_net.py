@@ -227,14 +227,15 @@ class Hierarchical_PoseGenerator(nn.Module):
                                   _LinearP(self.hidden_size // 2, pose_dim)])
         self.do_flatten_parameters = False
 
-    def forward(self, pre_seq, in_text, audio_feat_seq=None, vid_indices=None):
+    def forward(self, pre_seq, in_text, audio_feat_seq=None, vid_indices=None, _eps=None):
+        # _eps (not part of the reference signature): reparameterisation noise drawn by the caller
         text_feat_seq = self.text_encoder(in_text)
         assert audio_feat_seq.shape[1] == text_feat_seq.shape[1]
         assert vid_indices is not None
         z_context = self.speaker_embedding[1](self.speaker_embedding[0](vid_indices))
         z_mu = self.speaker_mu(z_context)
         z_logvar = self.speaker_logvar(z_context)
-        z_context = ops.reparameterize(z_mu, z_logvar)
+        z_context = ops.reparameterize(z_mu, z_logvar, _eps)
         in_data = ops.concat_seq(pre_seq, audio_feat_seq, text_feat_seq, z_context)
         output, _ = self.gru(in_data, None, sum_dirs=True)
         h = self.out[0](output.reshape(-1, output.shape[2]), ACT_LRELU)

@@ -336,9 +336,11 @@ class _ReparamFn(torch.autograd.Function):
         return dmu, dlv, None
 
 
-def reparameterize(mu, logvar):
-    """embedding_net.py:10-13; the noise draw comes from ha2g_b200.rng."""
-    eps = _rng.randn(mu.shape, mu.device)
+def reparameterize(mu, logvar, eps=None):
+    """embedding_net.py:10-13; the noise draw comes from ha2g_b200.rng unless the caller already drew it (the step
+    pre-draws in the reference's order when it batches two cascade passes into one)."""
+    if eps is None:
+        eps = _rng.randn(mu.shape, mu.device)
     return _ReparamFn.apply(mu, logvar, eps)
 
 

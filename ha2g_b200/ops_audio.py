@@ -16,6 +16,7 @@ _CONV_IMPL = os.environ.get("HA2G_CONV_IMPL", "tc")  # "tc": tcgen05 for stride-
 _CONV_PREC = 0 if os.environ.get("HA2G_CONV_PRECISION", "tf32x3") == "bf16x3" else 1
 
 
+_S2_TC = os.environ.get("HA2G_CONV_S2_TC", "1") != "0"   # stride-2 convolutions rewritten as stride-1 ones for tcgen05
 _WGRAD_IMPLICIT = os.environ.get("HA2G_WGRAD_IMPLICIT", "1") != "0"  # tap-shifted MN-major tcgen05 kernel for "same" convolutions
 _WGRAD_TC_MIN_CIN = int(os.environ.get("HA2G_WGRAD_TC_MIN_CIN", "64"))  # below: SIMT kernel (the stem has its own)
 _WGRAD_TC = os.environ.get("HA2G_WGRAD_IMPL", "tc") == "tc"  # weight gradient on the packed tcgen05 GEMM (bf16x3)
@@ -117,7 +118,79 @@ class _Conv2dFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class _PixelRemapFn(torch.autograd.Function):
+    """space-to-depth by 2 (mode 's2d') or every-second-pixel subsampling (mode 'sub') of an NHWC tensor."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        x = _c(x)
+        _chk(x)
+        N, H, W, C = x.shape
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        fn = "ha2g_space_to_depth2" if mode == "s2d" else "ha2g_subsample2"
+        y = torch.empty((N, H2, W2, 4 * C if mode == "s2d" else C), device=x.device, dtype=torch.float32)
+        _call(fn, _p(x), _p(y), N, H, W, C, 0, _st())
+        ctx.cfg = (N, H, W, C, fn)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C, fn = ctx.cfg
+        dy = _c(dy)
+        dx = torch.empty((N, H, W, C), device=dy.device, dtype=torch.float32)
+        _call(fn, _p(dy), _p(dx), N, H, W, C, 1, _st())
+        return dx, None
+
+
+class _S2WeightFn(torch.autograd.Function):
+    """3x3 stride-2 weight [Cout,C,3,3] -> the equivalent 2x2 stride-1 weight over the space-to-depth input [Cout,4C,2,2]."""
+
+    @staticmethod
+    def forward(ctx, w):
+        _chk(w)
+        Cout, C = w.shape[0], w.shape[1]
+        w2 = torch.empty((Cout, 4 * C, 2, 2), device=w.device, dtype=torch.float32)
+        _call("ha2g_conv_s2_weight", _p(w), _p(w2), Cout, C, 0, _st())
+        ctx.cfg = (Cout, C)
+        return w2
+
+    @staticmethod
+    def backward(ctx, dw2):
+        Cout, C = ctx.cfg
+        dw2 = _c(dw2)
+        dw = torch.empty((Cout, C, 3, 3), device=dw2.device, dtype=torch.float32)
+        _call("ha2g_conv_s2_weight", _p(dw2), _p(dw), Cout, C, 1, _st())
+        return dw
+
+
+class _CropFn(torch.autograd.Function):
+    """y[:, :Ho, :Wo, :] of an NHWC tensor as a contiguous tensor (and zero-padding in backward), via ha2g_copy_cols-free
+    strided copies of torch (data movement only)."""
+
+    @staticmethod
+    def forward(ctx, y, Ho, Wo):
+        ctx.shape = y.shape
+        return y[:, :Ho, :Wo, :].contiguous()
+
+    @staticmethod
+    def backward(ctx, d):
+        full = torch.zeros(ctx.shape, device=d.device, dtype=d.dtype)
+        full[:, :d.shape[1], :d.shape[2], :] = d
+        return full, None, None
+
+
 def conv2d(x, w, b=None, stride=1, pad=0):
+    """nn.Conv2d on NHWC activations.  The stride-2 convolutions of the encoder are rewritten as stride-1 convolutions
+    (3x3/pad 1 -> 2x2/pad 1 over the space-to-depth input with a remapped weight; 1x1 -> 1x1 over the subsampled input)
+    so that forward, data gradient and weight gradient all run on the tcgen05 kernels."""
+    KH = w.shape[2]
+    if stride == 2 and _CONV_IMPL == "tc" and _S2_TC and x.shape[3] % 8 == 0 and w.shape[0] % 4 == 0:
+        if KH == 1 and pad == 0:
+            return _Conv2dFn.apply(_PixelRemapFn.apply(x, "sub"), w, b, 1, 0)
+        if KH == 3 and pad == 1 and w.shape[3] == 3:
+            Ho, Wo = (x.shape[1] + 1) // 2, (x.shape[2] + 1) // 2
+            y = _Conv2dFn.apply(_PixelRemapFn.apply(x, "s2d"), _S2WeightFn.apply(w), b, 1, 1)
+            return _CropFn.apply(y, Ho, Wo)
     return _Conv2dFn.apply(x, w, b, stride, pad)
 
 

@@ -11,6 +11,8 @@ mechanical and result-preserving:
     computes then discards those gradients: dis_optimizer.zero_grad() precedes the next use);
   * loss terms are back-propagated as several roots with constant weights instead of being summed into
     one scalar first (identical gradients, no scalar arithmetic kernels);
+  * when both exist, those two no-grad cascades run as ONE cascade over 2B rows (``HA2G_BATCH_PASSES=0`` separates
+    them again); the random draws are made up front in the reference's order;
   * all ``.item()`` reads are packed into a single device->host copy at the end of the step;
   * after two eager calls per (modules, shapes, mode) signature the whole step -- forward, both backwards, the
     gradient all-reduce and the eight Adam updates, ~7 600 kernel launches -- is captured into ONE CUDA graph
@@ -24,8 +26,12 @@ from typing import Dict, List
 
 import torch
 
+import os
+
 from .. import cascade, dp, graph_step, ops_loss, rng
 from ..optim import fused_adam_step, zero_grad
+
+_BATCH_PASSES = os.environ.get("HA2G_BATCH_PASSES", "1") != "0"
 
 
 @contextlib.contextmanager
@@ -76,13 +82,37 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
     targets = cascade.split_targets(variant, target)
 
     scalars: Dict[str, torch.Tensor] = {}
+    B, L = target.shape[0], len(gens)
+    gan_on = epoch > warm_up_epochs and args.loss_gan_weight > 0.0
+    use_reg = (args.z_type == "speaker" or args.z_type == "random") and args.loss_reg_weight > 0.0
+    if use_reg and args.z_type != "speaker":
+        raise NotImplementedError("z_type='random' is not on the hierarchy configs' path")
+
+    # The two cascades whose outputs the reference detaches -- the discriminator-step pass and the mismatched-speaker
+    # pass of the diversity loss -- depend only on the (unchanged) generators, so they run as ONE no-grad cascade over
+    # 2B rows: half the launches, twice the rows per GEMM.  The draws are made up front in the reference's order
+    # (D-pass noise x L, G-pass noise x L, randperm, mismatched-pass noise x L).
+    batched = gan_on and use_reg and _BATCH_PASSES
+    eps_g = out_r_last = z_context_rand = None
+    if batched:
+        eps_d = [rng.randn((B, 16), dev) for _ in range(L)]
+        eps_g = [rng.randn((B, 16), dev) for _ in range(L)]
+        rand_vids = vid_indices[rng.randperm(B, vid_indices.device)]
+        eps_r = [rng.randn((B, 16), dev) for _ in range(L)]
 
     # ------------------------------------------------------------------ train D
-    gan_on = epoch > warm_up_epochs and args.loss_gan_weight > 0.0
     if gan_on:
         zero_grad(dis_optimizer)
         with torch.no_grad():
-            outs_d, _ = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat, vid_indices, n_pre)
+            if batched:
+                two = lambda t: torch.cat([t, t])
+                outs2, (z2, _, _) = cascade.run_cascade(
+                    variant, gens, [two(t) for t in targets], two(in_text_padded), [two(f.detach()) for f in linear_blend_feat],
+                    torch.cat([vid_indices, rand_vids]), n_pre, eps=[torch.cat([d, r]) for d, r in zip(eps_d, eps_r)])
+                outs_d = [outs2[-1][:B]]
+                out_r_last, z_context_rand = outs2[-1][B:], z2[B:]
+            else:
+                outs_d, _ = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat, vid_indices, n_pre)
         dis_real = discriminator(target, in_text_padded)
         dis_fake = discriminator(outs_d[-1].detach(), in_text_padded)
         l_real = ops_loss.neg_mean_log(dis_real)
@@ -116,7 +146,7 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
             -args.loss_contrastive_neg_weight)
 
     outs, (z_context, z_mu, z_logvar) = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat,
-                                                            vid_indices, n_pre)
+                                                            vid_indices, n_pre, eps=eps_g)
     out_dir_vec = outs[-1]
     for k, (o, t) in enumerate(zip(outs, targets)):
         add(f"huber{k}", ops_loss.huber(o, t, 0.1), args.loss_regression_weight)
@@ -125,16 +155,15 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
         dis_output = discriminator(out_dir_vec, in_text_padded)
     add("gen", ops_loss.neg_mean_log(dis_output), args.loss_gan_weight if epoch > warm_up_epochs else 0.0)
 
-    use_reg = (args.z_type == "speaker" or args.z_type == "random") and args.loss_reg_weight > 0.0
     if use_reg:
-        if args.z_type != "speaker":
-            raise NotImplementedError("z_type='random' is not on the hierarchy configs' path")
-        rand_idx = rng.randperm(vid_indices.shape[0], vid_indices.device)
-        rand_vids = vid_indices[rand_idx]
-        with torch.no_grad():
-            outs_r, (z_context_rand, _, _) = cascade.run_cascade(variant, gens, targets, in_text_padded,
-                                                                 linear_blend_feat, rand_vids, n_pre)
-        add("div_reg", ops_loss.div_reg(out_dir_vec, outs_r[-1], z_context, z_context_rand, 0.05), args.loss_reg_weight)
+        if not batched:
+            rand_idx = rng.randperm(vid_indices.shape[0], vid_indices.device)
+            rand_vids = vid_indices[rand_idx]
+            with torch.no_grad():
+                outs_r, (z_context_rand, _, _) = cascade.run_cascade(variant, gens, targets, in_text_padded,
+                                                                     linear_blend_feat, rand_vids, n_pre)
+            out_r_last = outs_r[-1]
+        add("div_reg", ops_loss.div_reg(out_dir_vec, out_r_last, z_context, z_context_rand, 0.05), args.loss_reg_weight)
         add("kld", ops_loss.kld(z_mu, z_logvar), args.loss_kld_weight)
 
     if args.loss_physical_weight > 0.0:

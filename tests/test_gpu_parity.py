@@ -415,3 +415,27 @@ def test_fused_dropout_kernel():
     # ragged length (scalar tail path)
     z = torch.ones(1001, device=DEV)
     assert abs(float((ops.dropout(z, 0.5, True) != 0).float().mean()) - 0.5) < 0.06
+
+
+@pytest.mark.parametrize("cfg", [(2, 16, 10, 32, 64, 3, 1), (2, 11, 7, 64, 128, 3, 1), (3, 9, 5, 128, 256, 3, 1),
+                                 (2, 16, 10, 32, 64, 1, 0), (2, 11, 7, 64, 128, 1, 0)])
+def test_conv_stride2_vs_torch(cfg):
+    """Stride-2 convolutions of the encoder (3x3/pad 1 block convolutions, 1x1 downsample) rewritten as stride-1
+    convolutions on the tensor-core kernels (space-to-depth / subsampling), odd sizes included, against torch fp64."""
+    from ha2g_b200 import ops_audio
+    N, H, W, Cin, Cout, K, pad = cfg
+    torch.manual_seed(5)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, K, K) / (Cin * K * K) ** 0.5
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xd, wd, None, stride=2, padding=pad)
+    g = torch.randn(y.shape)
+    (y * g.double()).sum().backward()
+    xg = x.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
+    wg = w.to(DEV).requires_grad_(True)
+    yg = ops_audio.conv2d(xg, wg, None, 2, pad)
+    assert tuple(yg.shape) == (N, y.shape[2], y.shape[3], Cout)
+    assert_close(yg.permute(0, 3, 1, 2), y, f"conv s2 fwd {cfg}", 3e-5)
+    (yg * g.permute(0, 2, 3, 1).contiguous().to(DEV)).sum().backward()
+    assert_close(xg.grad.permute(0, 3, 1, 2), xd.grad, f"conv s2 dgrad {cfg}", 3e-5)
+    assert_close(wg.grad, wd.grad, f"conv s2 wgrad {cfg}", 5e-5)
