@@ -145,8 +145,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = ha2g_warp_id();   // provably warp-uniform
     const int j0 = rank * HSP;
-    const float* __restrict__ W = p.w_hh[dir];
-    const float* __restrict__ b_hh = p.b_hh[dir];
+    // kernel parameters into registers up front: indexing the by-value struct dynamically (p.w_hh[dir]) would spill it to
+    // local memory and turn every global access below into a generic LD.E / ST.E behind an LDL
+    const float* __restrict__ W = dir ? p.w_hh[1] : p.w_hh[0];
+    const float* __restrict__ b_hh = dir ? p.b_hh[1] : p.b_hh[0];
+    const float* __restrict__ g_gi = p.gi;
+    float* __restrict__ g_y = p.y;
+    float* __restrict__ g_gates = p.gates;
+    long long* g_dbg = p.dbg;
+    const int g_flags = g_flags;
     const uint32_t tx_bytes = (uint32_t)(CL * L.slice_bytes);
 
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
@@ -199,7 +206,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
             __syncwarp();
         }
         if (nvalid > 0) mbw(bar_w, 0);
-        if (dbg_on && tid == 0) p.dbg[p.T * 8 + 1] = clock64();
+        if (dbg_on && tid == 0) g_dbg[p.T * 8 + 1] = clock64();
     }
     // shared -> TMEM: lane = gate row, 32-bit column c*4+i = the bf16 pair (k = 8c+2i, 8c+2i+1): the A-operand layout of
     // kind::f16 with A in tensor memory
@@ -232,7 +239,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    if (dbg_on && tid == 0) p.dbg[p.T * 8 + 2] = clock64();
+    if (dbg_on && tid == 0) g_dbg[p.T * 8 + 2] = clock64();
     // B descriptors: chunk stride (K direction, LBO) = 2*NB*16 (hi and lo of a chunk are adjacent), 8-row groups 128 B apart
     const uint32_t lbo = 2 * NB * 16;
     const uint64_t dbh0 = mkd(su32(hbuf), lbo, 128), dbl0 = mkd(su32(hbuf + NB * 16), lbo, 128);
@@ -269,18 +276,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
             if (T >= 3) mb_expect_tx(bar_full + 0, tx_bytes);
         }
         cluster.sync();
-        if (dbg_on && tid == 0) p.dbg[p.T * 8 + 3] = clock64();
+        if (dbg_on && tid == 0) g_dbg[p.T * 8 + 3] = clock64();
         for (int s = 0; s < T; ++s, ++it) {
             const int t = dir == 0 ? s : T - 1 - s;
             const int cur = s & 1;
             // ---- tensor core: D[128 x 16] = W_slice * h_{t-1}^T ------------------------------------------------
             if (warp == 0) {   // whole warp, converged; one elected lane issues
-                if (dbg_on && lane == 0) p.dbg[s * 8 + 7] = clock64();
+                if (dbg_on && lane == 0) g_dbg[s * 8 + 7] = clock64();
                 if (s > 0) {
                     mbw(bar_full + cur, cur ? full_ph1 : full_ph0);
                     if (cur) full_ph1 ^= 1; else full_ph0 ^= 1;
                 }
-                if (dbg_on && lane == 0) p.dbg[s * 8 + 0] = clock64();
+                if (dbg_on && lane == 0) g_dbg[s * 8 + 0] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (ha2g_elect_one()) {
                     if (s > 0 && s + 2 <= T - 1) mb_expect_tx(bar_full + cur, tx_bytes);   // h_{s+1} will land here
@@ -299,7 +306,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar_mma)) : "memory");
                 }
                 __syncwarp();
-                if (dbg_on && lane == 0) p.dbg[s * 8 + 1] = clock64();
+                if (dbg_on && lane == 0) g_dbg[s * 8 + 1] = clock64();
             }
             if (is_epi) {
                 // x-side pre-activations for this thread's 8 units (independent of the recurrence: issued before the wait)
@@ -311,7 +318,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                 for (int i = 0; i < 8; ++i) gir[i] = giz[i] = gin[i] = 0.f;
                 const bool full8 = jbase + 7 < H;   // whole 8-unit chunk valid -> 128-bit accesses (rows are 16-byte aligned)
                 if (live) {
-                    const float* g = p.gi + (((size_t)b * T + t) * 2 + dir) * 3 * H;
+                    const float* g = g_gi + (((size_t)b * T + t) * 2 + dir) * 3 * H;
                     if (full8) {
                         const float4 r0 = *reinterpret_cast<const float4*>(g + jbase), r1 = *reinterpret_cast<const float4*>(g + jbase + 4);
                         const float4 z0 = *reinterpret_cast<const float4*>(g + H + jbase), z1 = *reinterpret_cast<const float4*>(g + H + jbase + 4);
@@ -328,7 +335,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                     }
                 }
                 mbw(bar_mma, it & 1);
-                if (dbg_on && tid == 32) p.dbg[s * 8 + 2] = clock64();
+                if (dbg_on && tid == 32) g_dbg[s * 8 + 2] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 {   // TMEM -> shared: lane (gate row) q*32+lane holds 16 batch columns
                     uint32_t r[16];
@@ -346,7 +353,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps
-                if (dbg_on && tid == 32) p.dbg[s * 8 + 3] = clock64();
+                if (dbg_on && tid == 32) g_dbg[s * 8 + 3] = clock64();
                 float hnew[8], sr[8], sz[8], sn[8], shn[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) hnew[i] = sr[i] = sz[i] = sn[i] = shn[i] = 0.f;
@@ -375,7 +382,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
 #pragma unroll
                     for (int i = 0; i < 8; ++i) hown[(cc * 8 + i) * NB + bb] = hnew[i];
                 }
-                if (dbg_on && tid == 32) p.dbg[s * 8 + 4] = clock64();
+                if (dbg_on && tid == 32) g_dbg[s * 8 + 4] = clock64();
                 if (s < T - 1) {
                     // ---- push h_t: pack into this step's staging slice, then one bulk copy per destination CTA ----------
                     unsigned char* stg = stage + (size_t)cur * L.slice_bytes;
@@ -398,15 +405,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                         }
                         __syncwarp();
                     }
-                    if (dbg_on && tid == 32) p.dbg[s * 8 + 5] = clock64();
+                    if (dbg_on && tid == 32) g_dbg[s * 8 + 5] = clock64();
                 }
                 // ---- y and the saved gates: off the critical path (the next step's MMA is already being fed), staged
                 // through shared memory so that the global stores are 160-byte runs instead of 32 scattered sectors per
                 // instruction (the scattered version kept the LSU busy for ~1 000 cycles per step)
                 {
                     const int OR = L.orow;
-                    const int narr = p.gates != nullptr ? 5 : 1;
-                    if (has_item && !(p.flags & 2)) {
+                    const int narr = g_gates != nullptr ? 5 : 1;
+                    if (has_item && !(g_flags & 2)) {
                         float* o = outst + (size_t)bb * OR + cc * 8;
                         reinterpret_cast<float4*>(o)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
                         reinterpret_cast<float4*>(o)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
@@ -426,15 +433,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                     // copy-out: thread -> up to two fixed (batch row, float4) positions of every line group
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        if (k < co_n && !(p.flags & 1)) {
+                        if (k < co_n && !(g_flags & 1)) {
                             const int rb = co_rb[k], f4 = co_f4[k];
                             const int bg = m0 + rb, jg = j0 + f4 * 4;
                             if (bg < M && jg < H) {               // H % 4 == 0: a float4 is entirely valid or entirely padding
                                 const size_t row = (size_t)bg * T + t;
                                 const float* src = outst + (size_t)rb * OR + f4 * 4;
-                                *reinterpret_cast<float4*>(p.y + row * 2 * H + dir * H + jg) = *reinterpret_cast<const float4*>(src);
+                                *reinterpret_cast<float4*>(g_y + row * 2 * H + dir * H + jg) = *reinterpret_cast<const float4*>(src);
                                 if (narr == 5) {
-                                    float* gd = p.gates + (row * 2 + dir) * 4 * H + jg;
+                                    float* gd = g_gates + (row * 2 + dir) * 4 * H + jg;
 #pragma unroll
                                     for (int a = 1; a < 5; ++a)
                                         *reinterpret_cast<float4*>(gd + (size_t)(a - 1) * H) =
@@ -444,10 +451,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                         }
                     }
                 }
-                if (dbg_on && tid == 32) p.dbg[s * 8 + 6] = clock64();
+                if (dbg_on && tid == 32) g_dbg[s * 8 + 6] = clock64();
             }
         }
-        if (dbg_on && tid == 0) p.dbg[p.T * 8 + 4] = clock64();
+        if (dbg_on && tid == 0) g_dbg[p.T * 8 + 4] = clock64();
         // every CTA is past its last MMA (and hence past every copy into its buffers) before buffers are re-zeroed / freed
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         cluster.sync();

@@ -153,7 +153,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = ha2g_warp_id();
     const int j0 = rank * HSP;
-    const float* __restrict__ W = p.w_hh[dir];
+    // kernel parameters into registers up front (dynamic indexing of the by-value struct would spill it to local memory
+    // and make every global access a generic LD.E / ST.E behind an LDL)
+    const float* __restrict__ W = dir ? p.w_hh[1] : p.w_hh[0];
+    const float* __restrict__ g_dy = p.dy;
+    const float* __restrict__ g_y = p.y;
+    const float* __restrict__ g_gates = p.gates;
+    float* __restrict__ g_dgi = p.dgi;
+    float* __restrict__ g_dgh = p.dgh;
+    const int dy_ld = p.dy_ld, dy_ds = p.dy_dir_stride;
     const uint32_t tx_bytes = (uint32_t)(CL * L.slice_bytes);
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
     if (dbg_on && tid == 0) p.dbg[T * 8 + 0] = clock64();
@@ -287,10 +295,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
                 for (int i = 0; i < 8; ++i) r[i] = z[i] = n[i] = hn[i] = hp[i] = dyv[i] = 0.f;
                 const size_t row = (size_t)b * T + t;
                 if (live) {
-                    const float* gs = p.gates + (row * 2 + dir) * 4 * H + jbase;
+                    const float* gs = g_gates + (row * 2 + dir) * 4 * H + jbase;
                     ld8(gs, r, n4); ld8(gs + H, z, n4); ld8(gs + 2 * H, n, n4); ld8(gs + 3 * H, hn, n4);
-                    if (s > 0) ld8(p.y + ((size_t)b * T + tp) * 2 * H + dir * H + jbase, hp, n4);
-                    ld8(p.dy + row * p.dy_ld + dir * p.dy_dir_stride + jbase, dyv, n4);
+                    if (s > 0) ld8(g_y + ((size_t)b * T + tp) * 2 * H + dir * H + jbase, hp, n4);
+                    ld8(g_dy + row * dy_ld + dir * dy_ds + jbase, dyv, n4);
                 }
                 if (dbg_on && tid == 32) p.dbg[rd * 8 + 0] = clock64();
                 // ---- A: wait for the 8 partial products of dh_t, reduce, gate gradients ---------------------------------
@@ -387,8 +395,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
                             const size_t as = (size_t)NB * L.orow;
                             const float4 vr = *reinterpret_cast<const float4*>(src), vz = *reinterpret_cast<const float4*>(src + as);
                             const float4 vn = *reinterpret_cast<const float4*>(src + 2 * as), vnr = *reinterpret_cast<const float4*>(src + 3 * as);
-                            float* gi_o = p.dgi + (row * 2 + dir) * 3 * H + jg;
-                            float* gh_o = p.dgh + (row * 2 + dir) * 3 * H + jg;
+                            float* gi_o = g_dgi + (row * 2 + dir) * 3 * H + jg;
+                            float* gh_o = g_dgh + (row * 2 + dir) * 3 * H + jg;
                             *reinterpret_cast<float4*>(gi_o) = vr; *reinterpret_cast<float4*>(gi_o + H) = vz;
                             *reinterpret_cast<float4*>(gi_o + 2 * H) = vn;
                             *reinterpret_cast<float4*>(gh_o) = vr; *reinterpret_cast<float4*>(gh_o + H) = vz;
