@@ -109,6 +109,39 @@ def step_flops(variant, B, epoch_full=True):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def gru_kernel_roofline(dev, M, T=T_FRAMES, H=300, iters=24):
+    """Live CUDA-event timing of the fused GRU recurrence kernel (gru_seq_fwd_tc2_kernel, the kernel the north star
+    names) at the workload's shape, rotating over buffer sets larger than the 126 MB L2 between launches.
+    -> (average launch ms, algorithmic FLOPs per launch)."""
+    import torch
+    from ha2g_b200._lib import lib
+    from ha2g_b200 import ops
+    ops._ensure_workspace()
+    st = torch.cuda.current_stream().cuda_stream
+    sets = []
+    for _ in range(4):   # 4 x (gi 31 MB + y 10 MB + gates 42 MB) = 334 MB > L2
+        sets.append((torch.randn(M, T, 6 * H, device=dev), torch.empty(M, T, 2 * H, device=dev), torch.empty(M, T, 8 * H, device=dev)))
+    w = [torch.randn(3 * H, H, device=dev) * 0.05 for _ in range(2)]
+    b = [torch.randn(3 * H, device=dev) * 0.05 for _ in range(2)]
+    p = lambda t: t.data_ptr()
+
+    def launch(i):
+        gi, y, gates = sets[i % len(sets)]
+        rc = lib.ha2g_gru_seq_fwd_tc2(p(gi), p(w[0]), p(w[1]), p(b[0]), p(b[1]), p(y), p(gates), M, T, H, st)
+        assert rc is None or rc == 0
+    for i in range(4):
+        launch(i)
+    torch.cuda.synchronize()
+    evs = []
+    for i in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); launch(i); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b_) for a, b_ in evs) / len(evs)
+    return ms, 2.0 * M * T * 2 * (3 * H * H)
+
+
 def build_world(variant, device, seed=0):
     import torch
     from ha2g_b200.constants import make_args
@@ -288,6 +321,7 @@ def main():
         step(i, False)
     barrier()
     topstat = ops.profile_end().get(top, None)
+    kern_ms, kern_flops = gru_kernel_roofline(dev, a.batch) if rank == 0 else (None, None)
     if rank != 0:
         _finish_process(world)
         return
@@ -300,24 +334,35 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md 1.4 PF sustained)"
-    roofline = None
+    # dominant kernel = the fused GRU recurrence (gru_seq_fwd_tc2_kernel): 36 launches at M = B and 24 at M = 2B per step
+    achieved = kern_flops / (kern_ms * 1e-3) / 1e12
+    peak_burst = peaks.get("bf16_tflops", 1590.0)   # the kernel is timed alone: burst figure (recipe fallback 1.59 PF)
+    peak_burst_src = ("measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback (B200_PROFILING.md 1.59 PF burst)")
+    calls_per_step = (len(gens) * 4 * 2 + 4 * 3) if a.epoch > args.loss_warmup else len(gens) * 4 * 2
+    roofline = {"bound": "tensor", "kernel": "gru_seq_fwd_tc2_kernel (csrc/gru_cluster_tc2.cu), one bidirectional GRU layer, "
+                                             f"M={a.batch} rows x T=34 x H=300",
+                "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
+                "traffic": 39.1e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_f_ncu_full.md "
+                                                     "(algorithmic bytes per launch: 85.7e6)",
+                "peak_source": peak_burst_src, "us_per_launch": kern_ms * 1e3, "flops_per_launch": kern_flops,
+                "launches_per_step": calls_per_step,
+                "note": "algorithmic fp32-equivalent FLOPs of the recurrence (2*M*T*2*3H*H; the kernel issues 3 bf16 MMAs per "
+                        "product) / average CUDA-event time of 24 launches at the workload's shape, buffers rotated over 334 MB "
+                        "(> L2); the recurrence is latency-bound by design (34 dependent steps per launch)"}
+    top_launcher = None
     if topstat and topstat["calls"]:
-        achieved = topstat["flops"] / (topstat["ms"] * 1e-3) / 1e12 if topstat["ms"] > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                    "calls_timed": topstat["calls"], "ms_timed": topstat["ms"],
-                    "share_of_step": topstat["ms"] / ms if ms > 0 else None,
-                    "note": "achieved = algorithmic FLOPs of the launcher's calls / CUDA-event time of those calls over "
-                            f"{a.steps} eager passes of the same step right after the timed region (the timed region itself "
-                            "replays one CUDA graph, which has no per-kernel host events); fp32-accurate bf16x3 path "
-                            "measured against the dense bf16 tensor peak"}
+        la = topstat["flops"] / (topstat["ms"] * 1e-3) / 1e12 if topstat["ms"] > 0 else 0.0
+        top_launcher = {"launcher": top, "achieved_tflops": la, "frac": la / peak_tf, "calls_timed": topstat["calls"],
+                        "ms_timed": topstat["ms"], "share_of_step": topstat["ms"] / a.steps / (ms / a.steps) if ms > 0 else None,
+                        "note": f"C-ABI launcher with the largest CUDA-event time over {a.steps} eager passes of the same step "
+                                "right after the timed region (the timed region replays one CUDA graph)"}
     line = {"metric": metric, "value": frames * a.steps / (ms * 1e-3), "unit": "pose-frames/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": frames * a.steps / (ms_e2e * 1e-3), "unit": "pose-frames/s",
                     "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * (len(ret) + len(gens) + 2) * world},
             "gpu_launches": launches, "cuda_graph": {"enabled": graph_step.enabled(), **graph_step.STATS},
-            "clocks": clocks, "roofline": roofline,
+            "clocks": clocks, "roofline": roofline, "top_launcher": top_launcher,
             "step_tflops": step_flops(a.variant, a.batch * world) * a.steps / (ms * 1e-3) / 1e12,
             "last_losses": {k: round(v, 5) for k, v in ret.items()},
             "profile_top5": sorted(((k, round(v["ms"], 3), v["calls"]) for k, v in prof.items()), key=lambda r: -r[1])[:5]}
