@@ -251,7 +251,9 @@ __global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __res
                                                               const float* __restrict__ lse, float* __restrict__ part,
                                                               float* __restrict__ diag, float* __restrict__ dgrad,
                                                               const float* __restrict__ gscale, int N, int variant,
-                                                              int own_is_a, int cols_per_split) {
+                                                              int own_is_a, int cols_per_split, int Noth, int off) {
+    // rectangular form (data-parallel global batch): `own` has N rows, `oth` has Noth rows; the loss rows are always the
+    // rows of a, whose label is column (row + off) of b.  Square single-GPU case: Noth == N, off == 0.
     __shared__ float tile[CT][CC + 1];
     __shared__ float tlse[CT];
     const int i = blockIdx.x * CT + threadIdx.x;
@@ -259,14 +261,15 @@ __global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __res
     float me[CC];
 #pragma unroll
     for (int c = 0; c < CC; ++c) me[c] = valid ? own[(size_t)i * CC + c] : 0.f;
-    const int j_beg = blockIdx.y * cols_per_split, j_end = min(N, j_beg + cols_per_split);
+    const int j_beg = blockIdx.y * cols_per_split, j_end = min(Noth, j_beg + cols_per_split);
+    const int Na = own_is_a ? N : Noth;   // number of loss rows (rows of a)
     float m = -CUDART_INF_F, s = 0.f;
     float acc[CC];
     float my_lse = 0.f, gs = 0.f;
     if (MODE == 1) {
 #pragma unroll
         for (int c = 0; c < CC; ++c) acc[c] = 0.f;
-        gs = (gscale != nullptr ? *gscale : 1.f) / (float)N;
+        gs = (gscale != nullptr ? *gscale : 1.f) / (float)Na;
         if (own_is_a && valid) my_lse = lse[i];
     }
     for (int j0 = j_beg; j0 < j_end; j0 += CT) {
@@ -290,14 +293,15 @@ __global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __res
             const float d = sqrtf(d2);
             const float l = contrastive_logit(d, variant);
             const int j = j0 + r;
+            const bool is_diag = own_is_a ? (j == i + off) : (j + off == i);
             if (MODE == 0) {
-                if (j == i) diag[i] = l;
+                if (is_diag) diag[i] = l;
                 if (l > m) { s = s * expf(m - l) + 1.f; m = l; }
                 else s += expf(l - m);
             } else {
                 const float row_lse = own_is_a ? my_lse : tlse[r];
                 float p = expf(l - row_lse);
-                if (j == i) p -= 1.f;
+                if (is_diag) p -= 1.f;
                 float dld;
                 if (variant == 0) { float t = d + 1e-8f; dld = -1.f / (t * t); }
                 else dld = -1.f / (d * d);
@@ -386,13 +390,51 @@ HA2G_API int ha2g_physical(const float* out, float* grad, int64_t rows, int vari
     physical_kernel<<<ha2g_div_up(rows, 4), 128, 0, stream>>>(out, grad, rows, variant, nb, npairs, loss);
     HA2G_RETURN_LAST();
 }
-static int contrastive_splits(int N) {
-    int rows_ctas = (N + CT - 1) / CT;
-    int s = (148 * 2 + rows_ctas - 1) / rows_ctas;
-    int max_s = (N + CT - 1) / CT;
-    if (s > max_s) s = max_s;
-    if (s < 1) s = 1;
-    return s;
+extern "C" int ha2g_contrastive_fwd_rect(const float*, const float*, float*, float*, float*, float*, float*, float*, float*,
+                                         int, int, int, int, float*, cudaStream_t);
+extern "C" int ha2g_contrastive_bwd_rect(const float*, const float*, const float*, const float*, const float*, const float*,
+                                         float*, float*, float*, float*, int, int, int, int, cudaStream_t);
+// Rectangular SoftmaxContrastiveLoss for the data-parallel global batch (the reference computes the loss over the whole
+// DataParallel batch, scripts/train_expressive.py:184-197 + train_hierarchy_expressive.py:244-249): a [Na,32] are this
+// rank's rows, b [Nb,32] the all-gathered columns, row i's positive is column i + off (off = rank * Na).
+// loss ACCUMULATED += mean over the Na local rows.  part: [Na * ceil(Nb/128) * 2] floats (upper bound), diag/lse/na: [Na],
+// an [Na,32], bn [Nb,32], nb [Nb].
+HA2G_API int ha2g_contrastive_fwd_rect(const float* a, const float* b, float* an, float* bn, float* na, float* nb,
+                                       float* lse, float* part, float* diag, int Na, int Nb, int off, int variant,
+                                       float* loss, cudaStream_t stream) {
+    const int rows_ctas = ha2g_div_up(Na, CT);
+    int S = (148 * 2 + rows_ctas - 1) / rows_ctas;
+    const int max_s = ha2g_div_up(Nb, CT);
+    if (S > max_s) S = max_s;
+    if (S < 1) S = 1;
+    const int cols = ((Nb + S - 1) / S + CT - 1) / CT * CT;
+    l2norm_rows_kernel<<<ha2g_div_up(Na, 8), 256, 0, stream>>>(a, an, na, Na);
+    l2norm_rows_kernel<<<ha2g_div_up(Nb, 8), 256, 0, stream>>>(b, bn, nb, Nb);
+    dim3 grid(rows_ctas, ha2g_div_up(Nb, cols));
+    contrastive_pair_kernel<0><<<grid, CT, 0, stream>>>(an, bn, nullptr, part, diag, nullptr, nullptr, Na, variant, 1, cols, Nb, off);
+    contrastive_finalize_kernel<<<ha2g_div_up(Na, 256), 256, 0, stream>>>(part, diag, Na, grid.y, lse, loss);
+    HA2G_RETURN_LAST();
+}
+// Backward of the rectangular loss: da [Na,32] and db [Nb,32] (the gradient wrt ALL gathered columns: the caller
+// reduce-scatters it to the owning ranks) = gscale * d loss / d a, b.  dan [Na,32], dbn [Nb,32]: zero-initialised scratch.
+HA2G_API int ha2g_contrastive_bwd_rect(const float* an, const float* bn, const float* na, const float* nb, const float* lse,
+                                       const float* gscale, float* dan, float* dbn, float* da, float* db, int Na, int Nb,
+                                       int off, int variant, cudaStream_t stream) {
+    auto splits = [](int rows, int oth) {
+        const int rc = (rows + CT - 1) / CT;
+        int S = (148 * 2 + rc - 1) / rc;
+        const int mx = (oth + CT - 1) / CT;
+        if (S > mx) S = mx;
+        if (S < 1) S = 1;
+        return ((oth + S - 1) / S + CT - 1) / CT * CT;
+    };
+    const int cols_a = splits(Na, Nb), cols_b = splits(Nb, Na);
+    dim3 grid_a(ha2g_div_up(Na, CT), ha2g_div_up(Nb, cols_a)), grid_b(ha2g_div_up(Nb, CT), ha2g_div_up(Na, cols_b));
+    contrastive_pair_kernel<1><<<grid_a, CT, 0, stream>>>(an, bn, lse, nullptr, nullptr, dan, gscale, Na, variant, 1, cols_a, Nb, off);
+    contrastive_pair_kernel<1><<<grid_b, CT, 0, stream>>>(bn, an, lse, nullptr, nullptr, dbn, gscale, Nb, variant, 0, cols_b, Na, off);
+    l2norm_rows_bwd_kernel<<<ha2g_div_up(Na, 8), 256, 0, stream>>>(dan, an, na, da, Na);
+    l2norm_rows_bwd_kernel<<<ha2g_div_up(Nb, 8), 256, 0, stream>>>(dbn, bn, nb, db, Nb);
+    HA2G_RETURN_LAST();
 }
 // Streaming SoftmaxContrastiveLoss forward (replaces criterion(text_feat, feat_*) at
 // scripts/train_eval/train_hierarchy_expressive.py:244-249; class at train_hierarchy.py:23-68): L2-normalise rows,
@@ -402,25 +444,11 @@ static int contrastive_splits(int N) {
 // scratch: part [N * ceil(N/128) * 2] floats (upper bound), diag [N].
 HA2G_API int ha2g_contrastive_fwd(const float* a, const float* b, float* an, float* bn, float* na, float* nb, float* lse,
                                   float* part, float* diag, int N, int variant, float* loss, cudaStream_t stream) {
-    const int S = contrastive_splits(N);
-    const int cols = ((N + S - 1) / S + CT - 1) / CT * CT;
-    l2norm_rows_kernel<<<ha2g_div_up(N, 8), 256, 0, stream>>>(a, an, na, N);
-    l2norm_rows_kernel<<<ha2g_div_up(N, 8), 256, 0, stream>>>(b, bn, nb, N);
-    dim3 grid(ha2g_div_up(N, CT), ha2g_div_up(N, cols));
-    contrastive_pair_kernel<0><<<grid, CT, 0, stream>>>(an, bn, nullptr, part, diag, nullptr, nullptr, N, variant, 1, cols);
-    contrastive_finalize_kernel<<<ha2g_div_up(N, 256), 256, 0, stream>>>(part, diag, N, grid.y, lse, loss);
-    HA2G_RETURN_LAST();
+    return ha2g_contrastive_fwd_rect(a, b, an, bn, na, nb, lse, part, diag, N, N, 0, variant, loss, stream);
 }
 // Contrastive backward: da, db [N,32] = gscale * d loss/d a, d loss/d b.  dan, dbn: zero-initialised scratch [N,32].
 HA2G_API int ha2g_contrastive_bwd(const float* an, const float* bn, const float* na, const float* nb, const float* lse,
                                   const float* gscale, float* dan, float* dbn, float* da, float* db, int N, int variant,
                                   cudaStream_t stream) {
-    const int S = contrastive_splits(N);
-    const int cols = ((N + S - 1) / S + CT - 1) / CT * CT;
-    dim3 grid(ha2g_div_up(N, CT), ha2g_div_up(N, cols));
-    contrastive_pair_kernel<1><<<grid, CT, 0, stream>>>(an, bn, lse, nullptr, nullptr, dan, gscale, N, variant, 1, cols);
-    contrastive_pair_kernel<1><<<grid, CT, 0, stream>>>(bn, an, lse, nullptr, nullptr, dbn, gscale, N, variant, 0, cols);
-    l2norm_rows_bwd_kernel<<<ha2g_div_up(N, 8), 256, 0, stream>>>(dan, an, na, da, N);
-    l2norm_rows_bwd_kernel<<<ha2g_div_up(N, 8), 256, 0, stream>>>(dbn, bn, nb, db, N);
-    HA2G_RETURN_LAST();
+    return ha2g_contrastive_bwd_rect(an, bn, na, nb, lse, gscale, dan, dbn, da, db, N, N, 0, variant, stream);
 }

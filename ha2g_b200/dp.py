@@ -6,17 +6,21 @@ rank owns a full replica and its own B_local clips; after each backward the grad
 are averaged across ranks (bucketed flat all-reduce), so every replica applies the identical Adam update.
 BatchNorm statistics stay per-rank, exactly like DataParallel's per-replica statistics.
 
-Documented deviation: the contrastive loss is computed over each rank's own N = B_local*34 rows instead of the
-gathered global batch; c_pos/c_neg therefore differ from a single-process global-batch run by
-the log of the world size in their softmax normaliser.
+The contrastive loss runs over the GLOBAL batch like the reference's DataParallel step: each rank
+all-gathers the 32-wide audio features, evaluates its own rows against all columns, and reduce-scatters the column
+gradients (ops_loss._ContrastiveFn).  ``HA2G_DP_LOCAL_CONTRASTIVE=1`` keeps the loss rank-local (no collective in
+the loss; c_pos/c_neg then differ by the log of the world size in their softmax normaliser).
 """
 from __future__ import annotations
+
+import os
 
 from typing import List, Optional
 
 import torch
 
-_state = {"world": 1, "enabled": False}
+_state = {"world": 1, "enabled": False, "rank": 0,
+          "global_contrastive": os.environ.get("HA2G_DP_LOCAL_CONTRASTIVE", "0") != "1"}
 BUCKET_BYTES = 64 << 20
 
 
@@ -25,6 +29,7 @@ def enable(world_size: int, modules: Optional[List[torch.nn.Module]] = None, bro
     and buffers so all replicas start identical."""
     import torch.distributed as dist
     _state["world"], _state["enabled"] = world_size, world_size > 1
+    _state["rank"] = dist.get_rank() if world_size > 1 else 0
     if broadcast and modules and world_size > 1:
         for m in modules:
             for t in list(m.parameters()) + list(m.buffers()):
@@ -32,7 +37,15 @@ def enable(world_size: int, modules: Optional[List[torch.nn.Module]] = None, bro
 
 
 def disable():
-    _state["world"], _state["enabled"] = 1, False
+    _state["world"], _state["enabled"], _state["rank"] = 1, False, 0
+
+
+def rank() -> int:
+    return _state["rank"]
+
+
+def global_contrastive() -> bool:
+    return _state["enabled"] and _state["global_contrastive"]
 
 
 def world_size() -> int:

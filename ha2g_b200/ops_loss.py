@@ -160,41 +160,61 @@ def physical(out, variant: str, mean_dir_vec):
 
 
 class _ContrastiveFn(torch.autograd.Function):
+    """Streaming SoftmaxContrastiveLoss.  Under data parallelism (world > 1) the columns b are all-gathered so that the
+    loss runs over the GLOBAL batch like the reference's DataParallel step (local rows x global columns, positives at
+    rank*N + i), and the gradient wrt the gathered columns is reduce-scattered back to the ranks that own them."""
+
     @staticmethod
-    def forward(ctx, a, b, variant_id):
+    def forward(ctx, a, b, variant_id, world, rank):
         a, b = _c(a), _c(b)
         _chk(a, b)
         N, C = a.shape
         if C != 32 or b.shape != a.shape:
             raise RuntimeError("contrastive kernel expects two [N,32] feature matrices")
         dev = a.device
-        an, bn = torch.empty_like(a), torch.empty_like(b)
+        if world > 1:
+            import torch.distributed as dist
+            b_all = torch.empty((world * N, C), device=dev, dtype=torch.float32)
+            dist.all_gather_into_tensor(b_all, b)
+        else:
+            b_all = b
+        Nb = b_all.shape[0]
+        an, bn = torch.empty_like(a), torch.empty_like(b_all)
         na = torch.empty((N,), device=dev, dtype=torch.float32)
-        nb = torch.empty((N,), device=dev, dtype=torch.float32)
+        nb = torch.empty((Nb,), device=dev, dtype=torch.float32)
         lse = torch.empty((N,), device=dev, dtype=torch.float32)
-        S = (N + 127) // 128
+        S = (Nb + 127) // 128
         part = torch.empty((N * S * 2,), device=dev, dtype=torch.float32)
         diag = torch.empty((N,), device=dev, dtype=torch.float32)
         loss = torch.zeros((1,), device=dev, dtype=torch.float32)
-        _call("ha2g_contrastive_fwd", _p(a), _p(b), _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(part), _p(diag), N,
-              variant_id, _p(loss), _st())
-        ctx.variant_id = variant_id
+        _call("ha2g_contrastive_fwd_rect", _p(a), _p(b_all), _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(part), _p(diag), N, Nb,
+              rank * N, variant_id, _p(loss), _st())
+        ctx.cfg = (variant_id, world, rank)
         ctx.save_for_backward(an, bn, na, nb, lse)
         return loss
 
     @staticmethod
     def backward(ctx, dl):
         an, bn, na, nb, lse = ctx.saved_tensors
-        N = an.shape[0]
+        variant_id, world, rank = ctx.cfg
+        N, Nb = an.shape[0], bn.shape[0]
         dl = _c(dl)
         dan, dbn = torch.zeros_like(an), torch.zeros_like(bn)
-        da, db = torch.empty_like(an), torch.empty_like(bn)
-        _call("ha2g_contrastive_bwd", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(dl), _p(dan), _p(dbn), _p(da), _p(db), N,
-              ctx.variant_id, _st())
-        return da, db, None
+        da, db_all = torch.empty_like(an), torch.empty_like(bn)
+        _call("ha2g_contrastive_bwd_rect", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(dl), _p(dan), _p(dbn), _p(da), _p(db_all),
+              N, Nb, rank * N, variant_id, _st())
+        if world > 1:
+            import torch.distributed as dist
+            db = torch.empty_like(an)
+            dist.reduce_scatter_tensor(db, db_all, op=dist.ReduceOp.SUM)
+        else:
+            db = db_all
+        return da, db, None, None, None
 
 
 def contrastive(a, b, variant: str):
     """SoftmaxContrastiveLoss.forward without materialising the N x N x 32 tensor
     (train_hierarchy.py:54-68 gesture: 1/(D+1e-8) clamped; train_hierarchy_expressive.py:108-121: 1/D)."""
-    return _ContrastiveFn.apply(a, b, 0 if variant == "gesture" else 1)
+    from . import dp
+    world, rank = (dp.world_size(), dp.rank()) if dp.global_contrastive() else (1, 0)
+    return _ContrastiveFn.apply(a, b, 0 if variant == "gesture" else 1, world, rank)

@@ -439,3 +439,42 @@ def test_conv_stride2_vs_torch(cfg):
     (yg * g.permute(0, 2, 3, 1).contiguous().to(DEV)).sum().backward()
     assert_close(xg.grad.permute(0, 3, 1, 2), xd.grad, f"conv s2 dgrad {cfg}", 3e-5)
     assert_close(wg.grad, wd.grad, f"conv s2 wgrad {cfg}", 5e-5)
+
+
+@pytest.mark.parametrize("variant", ["gesture", "expressive"])
+def test_contrastive_rectangular_matches_square(variant):
+    """The data-parallel form of the contrastive loss (local rows x all-gathered columns, positives at rank*N + i,
+    column gradients summed over ranks) must reproduce the single-process loss over the whole batch: emulate W ranks
+    on one GPU through the rectangular launchers and compare with the square path (itself pinned to the oracle)."""
+    from ha2g_b200 import ops_loss
+    from ha2g_b200.ops import _call, _p, _st
+    torch.manual_seed(11)
+    W, Nl = 3, 170
+    N = W * Nl
+    a = torch.randn(N, 32, device=DEV, requires_grad=True)
+    b = torch.randn(N, 32, device=DEV, requires_grad=True)
+    full = ops_loss.contrastive(a, b, variant)
+    full.backward()
+    vid = 0 if variant == "gesture" else 1
+    loss_sum, da_parts, db_sum = 0.0, [], torch.zeros(N, 32, device=DEV)
+    for r in range(W):
+        ar = a.detach()[r * Nl:(r + 1) * Nl].contiguous()
+        ba = b.detach().contiguous()
+        an, bn = torch.empty_like(ar), torch.empty_like(ba)
+        na, nb, lse, diag = (torch.empty(Nl, device=DEV), torch.empty(N, device=DEV), torch.empty(Nl, device=DEV),
+                             torch.empty(Nl, device=DEV))
+        part = torch.empty(Nl * ((N + 127) // 128) * 2, device=DEV)
+        loss = torch.zeros(1, device=DEV)
+        _call("ha2g_contrastive_fwd_rect", _p(ar), _p(ba), _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(part), _p(diag), Nl, N,
+              r * Nl, vid, _p(loss), _st())
+        dan, dbn = torch.zeros_like(an), torch.zeros_like(bn)
+        da, db = torch.empty_like(an), torch.empty_like(bn)
+        one = torch.ones(1, device=DEV)
+        _call("ha2g_contrastive_bwd_rect", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(one), _p(dan), _p(dbn), _p(da), _p(db),
+              Nl, N, r * Nl, vid, _st())
+        loss_sum += float(loss)
+        da_parts.append(da)
+        db_sum += db
+    assert abs(loss_sum / W - float(full)) <= 1e-5 * max(1.0, abs(float(full)))
+    assert_close(torch.cat(da_parts) / W, a.grad, f"rect contrastive da {variant}", 1e-4)
+    assert_close(db_sum / W, b.grad, f"rect contrastive db {variant}", 1e-4)
