@@ -261,8 +261,13 @@ HA2G_API int ha2g_gru_layer_bwd(const float* dy, int dy_ld, int dy_dir_stride, c
     }
     const int split = 4;
     // dW_ih_dir += dgi[:,dir]^T x            ([3H, MT] x [MT, I])
-    HA2G_CHECK(ha2g_gemm(dgi, x, dw_ih_f, nullptr, 3 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
-    HA2G_CHECK(ha2g_gemm(dgi + 3 * H, x, dw_ih_r, nullptr, 3 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
+    if (dw_ih_r == dw_ih_f + (size_t)3 * H * I) {
+        // the two directions' gradients are adjacent: one [6H x MT] x [MT x I] GEMM, x packed once
+        HA2G_CHECK(ha2g_gemm(dgi, x, dw_ih_f, nullptr, 6 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
+    } else {
+        HA2G_CHECK(ha2g_gemm(dgi, x, dw_ih_f, nullptr, 3 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
+        HA2G_CHECK(ha2g_gemm(dgi + 3 * H, x, dw_ih_r, nullptr, 3 * H, I, MT, 6 * H, I, I, 1, 0, 0, 1, split, stream));
+    }
     // dW_hh_f += sum_{m,t>=1} dgh[m,t,0]^T y[m,t-1,0:H];  dW_hh_r += sum_{m,t<=T-2} dgh[m,t,1]^T y[m,t+1,H:2H]
     if (T > 1) {
         HA2G_CHECK(ha2g_gemm_kseg(dgh + (size_t)6 * H, y, dw_hh_f, nullptr, 3 * H, H, M * (T - 1), 6 * H, 2 * H, H, 1,
@@ -271,10 +276,18 @@ HA2G_API int ha2g_gru_layer_bwd(const float* dy, int dy_ld, int dy_dir_stride, c
                                       2 * H, H, 1, 0, 0, 1, split, T - 1, T, stream));
     }
     // biases: column sums over all (m,t) rows
-    HA2G_CHECK(ha2g_col_sum(dgi, MT, 3 * H, 6 * H, db_ih_f, stream));
-    HA2G_CHECK(ha2g_col_sum(dgi + 3 * H, MT, 3 * H, 6 * H, db_ih_r, stream));
-    HA2G_CHECK(ha2g_col_sum(dgh, MT, 3 * H, 6 * H, db_hh_f, stream));
-    HA2G_CHECK(ha2g_col_sum(dgh + 3 * H, MT, 3 * H, 6 * H, db_hh_r, stream));
+    if (db_ih_r == db_ih_f + 3 * H) {
+        HA2G_CHECK(ha2g_col_sum(dgi, MT, 6 * H, 6 * H, db_ih_f, stream));
+    } else {
+        HA2G_CHECK(ha2g_col_sum(dgi, MT, 3 * H, 6 * H, db_ih_f, stream));
+        HA2G_CHECK(ha2g_col_sum(dgi + 3 * H, MT, 3 * H, 6 * H, db_ih_r, stream));
+    }
+    if (db_hh_r == db_hh_f + 3 * H) {
+        HA2G_CHECK(ha2g_col_sum(dgh, MT, 6 * H, 6 * H, db_hh_f, stream));
+    } else {
+        HA2G_CHECK(ha2g_col_sum(dgh, MT, 3 * H, 6 * H, db_hh_f, stream));
+        HA2G_CHECK(ha2g_col_sum(dgh + 3 * H, MT, 3 * H, 6 * H, db_hh_r, stream));
+    }
     // dx = dgi_f W_ih_f + dgi_r W_ih_r            ([MT,3H] x [3H,I])
     if (dx != nullptr) {
         HA2G_CHECK(ha2g_gemm(dgi, w_ih_f, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 0, 1, stream));

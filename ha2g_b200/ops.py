@@ -458,7 +458,13 @@ class _BiGRUFn(torch.autograd.Function):
             xin, y, gates = saved[3 * l:3 * l + 3]
             w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = weights[8 * l:8 * l + 8]
             I = xin.shape[2]
-            g = [torch.zeros_like(w) for w in weights[8 * l:8 * l + 8]]
+            # both directions' gradients of one kind live in ONE buffer: the launcher then needs a single GEMM for
+            # dW_ih (dgi^T x over all 6H gate columns) and a single column sum per bias pair, and 4 zero-fills, not 8
+            gw_ih = torch.zeros((2,) + tuple(w_ih.shape), device=dev, dtype=torch.float32)
+            gw_hh = torch.zeros((2,) + tuple(w_hh.shape), device=dev, dtype=torch.float32)
+            gb_ih = torch.zeros((2,) + tuple(b_ih.shape), device=dev, dtype=torch.float32)
+            gb_hh = torch.zeros((2,) + tuple(b_hh.shape), device=dev, dtype=torch.float32)
+            g = [gw_ih[0], gw_hh[0], gb_ih[0], gb_hh[0], gw_ih[1], gw_hh[1], gb_ih[1], gb_hh[1]]
             need_dx = l > 0 or ctx.needs_input_grad[0]
             dx = torch.empty((M, T, I), device=dev, dtype=torch.float32) if need_dx else None
             _call("ha2g_gru_layer_bwd", _p(dy), dy_ld, dy_ds, _p(xin), I, _p(y), _p(gates), _p(w_ih), _p(w_ih_r),
