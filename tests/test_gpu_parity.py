@@ -478,3 +478,12 @@ def test_contrastive_rectangular_matches_square(variant):
     assert abs(loss_sum / W - float(full)) <= 1e-5 * max(1.0, abs(float(full)))
     assert_close(torch.cat(da_parts) / W, a.grad, f"rect contrastive da {variant}", 1e-4)
     assert_close(db_sum / W, b.grad, f"rect contrastive db {variant}", 1e-4)
+
+
+@pytest.mark.parametrize("variant,B", [("gesture", 1), ("gesture", 5), ("expressive", 3)])
+def test_step_vs_oracle_ragged_batches(variant, B):
+    """Whole training step against the CPU oracle at batch sizes that leave every 16-row GRU chunk, 128-row GEMM tile and
+    64-pixel convolution block ragged (B = 1: a single clip; BatchNorm1d/2d over one sample)."""
+    from smoke_impl import run_smoke
+    ret, ref = run_smoke(variant, B, verbose=False)
+    assert set(ret) == set(ref)
