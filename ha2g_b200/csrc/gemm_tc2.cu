@@ -213,12 +213,17 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
     } else {
         // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
         if (nkb > 0) {
             mb_wait(bar_done, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const bool split = gridDim.z > 1;
+        // The accumulator arrives one ROW per thread (TMEM lane = row).  Writing it out that way makes every store
+        // instruction touch 32 different lines; instead each warp transposes its 32 x 32 block through shared memory (the
+        // operand ring is idle once bar_done has fired) and writes 128 contiguous bytes per row: 8x fewer L1 wavefronts.
+        constexpr int SP = 36;   // staging row pitch in floats: 16-byte aligned rows, conflict-free 128-bit accesses
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * SP;
+        const int rr4 = lane >> 3, c4 = lane & 7;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -238,44 +243,50 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
 #pragma unroll
                 for (int i = 0; i < 32; ++i) r[i] = 0u;
             }
-            if (row < M) {
-                float* crow = C + (size_t)row * ldc;
-                const bool vec = !split && ((ldc & 3) == 0) && (n0 + c0 + 32 <= N) && ((((uintptr_t)C) & 15) == 0) &&
-                                 (bias == nullptr || (((uintptr_t)bias) & 15) == 0);
-                if (vec) {
+            if (n0 + c0 >= N) continue;   // warp-uniform: nothing of this block is inside C
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const int col = n0 + c0 + i;
-                        float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                                               __uint_as_float(r[i + 3]));
-                        if (bias != nullptr) {
-                            const float4 bv = *reinterpret_cast<const float4*>(bias + col);
-                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                        }
-                        v.x = ha2g_act(v.x, act); v.y = ha2g_act(v.y, act); v.z = ha2g_act(v.z, act); v.w = ha2g_act(v.w, act);
-                        float4* dst = reinterpret_cast<float4*>(crow + col);
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<uint4*>(stg + (size_t)lane * SP + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+            __syncwarp();
+            const bool vec = !split && ((ldc & 3) == 0) && (n0 + c0 + 32 <= N) && ((((uintptr_t)C) & 15) == 0) &&
+                             (bias == nullptr || (((uintptr_t)bias) & 15) == 0);
+            if (vec) {
+                const int col = n0 + c0 + c4 * 4;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr) bv = *reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rl = it * 4 + rr4, grow = m0 + q * 32 + rl;
+                    if (grow < M) {
+                        float4 v = *reinterpret_cast<const float4*>(stg + (size_t)rl * SP + c4 * 4);
+                        v.x = ha2g_act(v.x + bv.x, act); v.y = ha2g_act(v.y + bv.y, act);
+                        v.z = ha2g_act(v.z + bv.z, act); v.w = ha2g_act(v.w + bv.w, act);
+                        float4* dst = reinterpret_cast<float4*>(C + (size_t)grow * ldc + col);
                         if (accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                         *dst = v;
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = n0 + c0 + i;
-                        if (col < N) {
-                            float v = __uint_as_float(r[i]);
-                            if (split) {
-                                if (bias != nullptr && blockIdx.z == 0) v += bias[col];
-                                atomicAdd(crow + col, v);
-                            } else {
-                                if (bias != nullptr) v += bias[col];
+                }
+            } else {
+                const int col = n0 + c0 + lane;
+                if (col < N) {
+                    const float bvs = (bias != nullptr && (!split || blockIdx.z == 0)) ? bias[col] : 0.f;
+#pragma unroll 4
+                    for (int rl = 0; rl < 32; ++rl) {
+                        const int grow = m0 + q * 32 + rl;
+                        if (grow < M) {
+                            float v = stg[(size_t)rl * SP + lane] + bvs;
+                            float* dst = C + (size_t)grow * ldc + col;
+                            if (split) atomicAdd(dst, v);
+                            else {
                                 v = ha2g_act(v, act);
-                                if (accumulate) v += crow[col];
-                                crow[col] = v;
+                                if (accumulate) v += *dst;
+                                *dst = v;
                             }
                         }
                     }
                 }
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
