@@ -293,7 +293,15 @@ __global__ void __launch_bounds__(CNT) conv_tc_kernel(const uint4* __restrict__ 
             ho = hp - g.pad; wo = wp - g.pad;
             valid = ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo;
         }
-        float* orow = out + (((size_t)n * g.Ho + ho) * g.Wo + wo) * g.Cd;
+        // The accumulator arrives one output PIXEL per thread.  Each warp transposes its 32 pixels x 32 channels through
+        // shared memory (halo block and weight ring are idle once bar_done has fired) so that 8 consecutive lanes write the
+        // 128 contiguous bytes of one pixel instead of every lane writing to a different pixel.
+        constexpr int SP = 36;   // staging pitch (floats): 16-byte aligned rows, conflict-free 128-bit accesses
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * SP;
+        long long* optr = reinterpret_cast<long long*>(smem + (size_t)4 * 32 * SP * 4) + (warp - 2) * 32;
+        optr[lane] = valid ? (long long)((((size_t)n * g.Ho + ho) * g.Wo + wo) * g.Cd) : -1ll;
+        __syncwarp();
+        const int rr4 = lane >> 3, c4 = lane & 7;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -308,20 +316,27 @@ __global__ void __launch_bounds__(CNT) conv_tc_kernel(const uint4* __restrict__ 
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (valid) {
+            if (n0 + c0 >= g.Cd) continue;   // warp-uniform
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const int col = n0 + c0 + i;
-                    if (col < g.Cd) {   // Cd % 4 == 0
-                        float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                                               __uint_as_float(r[i + 3]));
-                        if (bias != nullptr) {
-                            v.x += bias[col]; v.y += bias[col + 1]; v.z += bias[col + 2]; v.w += bias[col + 3];
-                        }
-                        *reinterpret_cast<float4*>(orow + col) = v;
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<uint4*>(stg + (size_t)lane * SP + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+            __syncwarp();
+            const int col = n0 + c0 + c4 * 4;
+            if (col < g.Cd) {   // Cd % 4 == 0
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr) bv = make_float4(bias[col], bias[col + 1], bias[col + 2], bias[col + 3]);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rl = it * 4 + rr4;
+                    const long long off = optr[rl];
+                    if (off >= 0) {
+                        float4 v = *reinterpret_cast<const float4*>(stg + (size_t)rl * SP + c4 * 4);
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        *reinterpret_cast<float4*>(out + off + col) = v;
                     }
                 }
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
