@@ -12,6 +12,7 @@
 // The data gradient is the same kernel run on the packed output gradient with flipped / transposed packed weights.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace {
 
@@ -255,19 +256,22 @@ __global__ void __launch_bounds__(CNT) conv_tc_kernel(const uint4* __restrict__ 
             for (int ab = 0; ab < n_ablk; ++ab) {
                 cmb_wait(bar_afull, ab & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // descriptors differ only in their 14-bit start-address field (units of 16 bytes): build them once and add
+                // offsets -- with N <= 64 an MMA is 16-32 cycles of tensor work, so the issue loop must not cost more
+                const uint64_t da_hi0 = cdesc(cs32(sa_hi), lbo_a, 128), da_lo0 = cdesc(cs32(sa_lo), lbo_a, 128);
+                const uint64_t dw0 = cdesc(cs32(sw), BN * 16, 128);
                 for (int tap = 0; tap < taps; ++tap) {
                     const int roff = (tap / g.KW) * g.Wp + (tap % g.KW);   // tap row offset inside the halo block
                     for (int sb = 0; sb < subs; ++sb, ++wit) {
                         const int st = wit % CWST;
                         cmb_wait(bar_wfull + st, (wit / CWST) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t w_hi = cs32(sw + (size_t)st * 2 * W_HALF), w_lo = w_hi + W_HALF;
+                        const uint64_t dwh = dw0 + (uint64_t)(st * ((2 * W_HALF) >> 4)), dwl = dwh + (uint64_t)(W_HALF >> 4);
+                        const uint64_t a_add = (uint64_t)((sb * CSUB) * g.RA + roff);
 #pragma unroll
                         for (int ks = 0; ks < CSUB / 2; ++ks) {
-                            const uint32_t a_off = (uint32_t)(((sb * CSUB + ks * 2) * g.RA + roff) * 16);
-                            const uint64_t dah = cdesc(cs32(sa_hi) + a_off, lbo_a, 128), dal = cdesc(cs32(sa_lo) + a_off, lbo_a, 128);
-                            const uint32_t b_off = (uint32_t)(ks * 2 * BN * 16);
-                            const uint64_t dbh = cdesc(w_hi + b_off, BN * 16, 128), dbl = cdesc(w_lo + b_off, BN * 16, 128);
+                            const uint64_t dah = da_hi0 + a_add + (uint64_t)(ks * 2 * g.RA), dal = da_lo0 + a_add + (uint64_t)(ks * 2 * g.RA);
+                            const uint64_t dbh = dwh + (uint64_t)(ks * 2 * BN), dbl = dwl + (uint64_t)(ks * 2 * BN);
                             cmma<TF32>(tmem_d, dah, dbh, idesc, first ? 0u : 1u);
                             first = 0;
                             cmma<TF32>(tmem_d, dah, dbl, idesc, 1u);
@@ -344,6 +348,209 @@ __global__ void __launch_bounds__(CNT) conv_tc_kernel(const uint4* __restrict__ 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN < 32 ? 32 : BN));
 }
 
+// ---- persistent variant ------------------------------------------------------------------------------------------
+// One CTA per SM walks the output tiles (128 positions each) round-robin.  Compared with one short-lived CTA per tile
+// (barrier init + TMEM allocation + an exposed halo-block load latency + an exposed epilogue for ~3 us of tensor work):
+//   * halo blocks are double-buffered (block = 8 channel chunks), so the next tile's activation is in flight while the
+//     current one is multiplied; the weight ring simply keeps streaming across tiles;
+//   * two TMEM accumulators alternate, so the epilogue of tile i (TMEM -> shared transpose -> coalesced stores) runs
+//     under the MMAs of tile i+1.
+// shared memory: A[2] (hi | lo) | W ring | epilogue staging + pixel offsets | barriers
+constexpr int CPB = 8;      // channel chunks per resident halo block in the persistent kernel
+
+template <int BN, bool TF32>
+__global__ void __launch_bounds__(CNT, 1) conv_tc_persist_kernel(const uint4* __restrict__ a_hi, const uint4* __restrict__ a_lo,
+                                                                 const uint4* __restrict__ b_hi, const uint4* __restrict__ b_lo,
+                                                                 const float* __restrict__ bias, float* __restrict__ out,
+                                                                 ConvTcGeom g, int tiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int a_bytes = g.cb * g.RA * 16;                      // one of hi / lo of one halo block
+    constexpr int W_HALF = CSUB * BN * 16;
+    constexpr int SP = 36;
+    constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+    unsigned char* sa = smem;                                  // [2][hi | lo]
+    unsigned char* sw = smem + 4 * (size_t)a_bytes;
+    float* stg_base = reinterpret_cast<float*>(sw + CWST * 2 * W_HALF);
+    long long* optr_base = reinterpret_cast<long long*>(stg_base + 4 * 32 * SP);
+    uint64_t* bar_afull = reinterpret_cast<uint64_t*>(optr_base + 4 * 32);   // [2]
+    uint64_t* bar_aempty = bar_afull + 2;       // [2]
+    uint64_t* bar_wfull = bar_aempty + 2;       // [CWST]
+    uint64_t* bar_wempty = bar_wfull + CWST;    // [CWST]
+    uint64_t* bar_cfull = bar_wempty + CWST;    // [2] accumulator ready
+    uint64_t* bar_cempty = bar_cfull + 2;       // [2] accumulator drained (4 epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_cempty + 2);
+
+    const int tid = threadIdx.x, warp = ha2g_warp_id(), lane = tid & 31;
+    const int n0 = blockIdx.x * BN;
+    const int taps = g.KH * g.KW;
+    const int n_ablk = g.cs_chunks / g.cb;
+    const int subs = g.cb / CSUB;
+    const int min_off = -(g.pad * g.Wp + g.pad);
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { cmb_init(bar_afull + i, 1); cmb_init(bar_aempty + i, 1); cmb_init(bar_cfull + i, 1); cmb_init(bar_cempty + i, 4); }
+        for (int i = 0; i < CWST; ++i) { cmb_init(bar_wfull + i, 1); cmb_init(bar_wempty + i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cs32(tmem_slot)), "r"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        if (ha2g_elect_one()) {
+            int wit = 0, ai = 0;
+            for (int tile = blockIdx.y; tile < tiles; tile += gridDim.y) {
+                const int q0 = g.guard + tile * CBM;
+                for (int ab = 0; ab < n_ablk; ++ab, ++ai) {
+                    const int buf = ai & 1;
+                    if (ai >= 2) cmb_wait(bar_aempty + buf, ((ai >> 1) - 1) & 1);
+                    unsigned char* sa_hi = sa + (size_t)buf * 2 * a_bytes;
+                    unsigned char* sa_lo = sa_hi + a_bytes;
+                    cmb_expect(bar_afull + buf, (uint32_t)(2 * a_bytes));
+                    for (int c = 0; c < g.cb; ++c) {
+                        const size_t src = (size_t)(ab * g.cb + c) * g.rows_pa + (size_t)(q0 + min_off);
+                        cbulk(sa_hi + (size_t)c * g.RA * 16, a_hi + src, (uint32_t)(g.RA * 16), bar_afull + buf);
+                        cbulk(sa_lo + (size_t)c * g.RA * 16, a_lo + src, (uint32_t)(g.RA * 16), bar_afull + buf);
+                    }
+                    for (int tap = 0; tap < taps; ++tap) {
+                        for (int sb = 0; sb < subs; ++sb, ++wit) {
+                            const int st = wit % CWST;
+                            if (wit >= CWST) cmb_wait(bar_wempty + st, ((wit / CWST) - 1) & 1);
+                            unsigned char* w_hi = sw + (size_t)st * 2 * W_HALF;
+                            unsigned char* w_lo = w_hi + W_HALF;
+                            cmb_expect(bar_wfull + st, 2 * W_HALF);
+#pragma unroll
+                            for (int c = 0; c < CSUB; ++c) {
+                                const size_t kc = (size_t)tap * g.cs_chunks + (size_t)ab * g.cb + sb * CSUB + c;
+                                cbulk(w_hi + c * (BN * 16), b_hi + kc * g.rows_pb + n0, BN * 16, bar_wfull + st);
+                                cbulk(w_lo + c * (BN * 16), b_lo + kc * g.rows_pb + n0, BN * 16, bar_wfull + st);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (ha2g_elect_one()) {
+            const uint32_t fmt = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CBM >> 4) << 24);
+            const uint32_t lbo_a = (uint32_t)(g.RA * 16);
+            int wit = 0, ai = 0, ti = 0;
+            for (int tile = blockIdx.y; tile < tiles; tile += gridDim.y, ++ti) {
+                const int cb_ = ti & 1;
+                if (ti >= 2) cmb_wait(bar_cempty + cb_, ((ti >> 1) - 1) & 1);   // the epilogue drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t dcol = tmem_d + (uint32_t)(cb_ * BN);
+                uint32_t first = 1;
+                for (int ab = 0; ab < n_ablk; ++ab, ++ai) {
+                    const int buf = ai & 1;
+                    cmb_wait(bar_afull + buf, (ai >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa_hi = cs32(sa + (size_t)buf * 2 * a_bytes), sa_lo = sa_hi + a_bytes;
+                    const uint64_t da_hi0 = cdesc(sa_hi, lbo_a, 128), da_lo0 = cdesc(sa_lo, lbo_a, 128);
+                    const uint64_t dw0 = cdesc(cs32(sw), BN * 16, 128);
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const int roff = (tap / g.KW) * g.Wp + (tap % g.KW);
+                        for (int sb = 0; sb < subs; ++sb, ++wit) {
+                            const int st = wit % CWST;
+                            cmb_wait(bar_wfull + st, (wit / CWST) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint64_t dwh = dw0 + (uint64_t)(st * ((2 * W_HALF) >> 4)), dwl = dwh + (uint64_t)(W_HALF >> 4);
+                            const uint64_t a_add = (uint64_t)((sb * CSUB) * g.RA + roff);
+#pragma unroll
+                            for (int ks = 0; ks < CSUB / 2; ++ks) {
+                                const uint64_t dah = da_hi0 + a_add + (uint64_t)(ks * 2 * g.RA), dal = da_lo0 + a_add + (uint64_t)(ks * 2 * g.RA);
+                                const uint64_t dbh = dwh + (uint64_t)(ks * 2 * BN), dbl = dwl + (uint64_t)(ks * 2 * BN);
+                                cmma<TF32>(dcol, dah, dbh, idesc, first ? 0u : 1u);
+                                first = 0;
+                                cmma<TF32>(dcol, dah, dbl, idesc, 1u);
+                                cmma<TF32>(dcol, dal, dbh, idesc, 1u);
+                            }
+                            ccommit(bar_wempty + st);
+                        }
+                    }
+                    ccommit(bar_aempty + buf);
+                }
+                ccommit(bar_cfull + cb_);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int qd = warp & 3;
+        float* stg = stg_base + (size_t)(warp - 2) * 32 * SP;
+        long long* optr = optr_base + (warp - 2) * 32;
+        const int rr4 = lane >> 3, c4 = lane & 7;
+        int ti = 0;
+        for (int tile = blockIdx.y; tile < tiles; tile += gridDim.y, ++ti) {
+            const int cb_ = ti & 1;
+            const int q = tile * CBM + qd * 32 + lane;      // padded position (without guard)
+            bool valid = q < g.N * g.Hp * g.Wp;
+            int n = 0, ho = 0, wo = 0;
+            if (valid) {
+                const int wp = q % g.Wp, hp = (q / g.Wp) % g.Hp;
+                n = q / (g.Wp * g.Hp);
+                ho = hp - g.pad; wo = wp - g.pad;
+                valid = ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo;
+            }
+            __syncwarp();
+            optr[lane] = valid ? (long long)((((size_t)n * g.Ho + ho) * g.Wo + wo) * g.Cd) : -1ll;
+            __syncwarp();
+            cmb_wait(bar_cfull + cb_, (ti >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cb_ * BN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 >= BN) {   // the accumulator is in registers: hand it back to the MMA warp (one arrival per warp)
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cs32(bar_cempty + cb_)) : "memory");
+                }
+                if (n0 + c0 >= g.Cd) continue;   // warp-uniform
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<uint4*>(stg + (size_t)lane * SP + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                __syncwarp();
+                const int col = n0 + c0 + c4 * 4;
+                if (col < g.Cd) {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias != nullptr) bv = make_float4(bias[col], bias[col + 1], bias[col + 2], bias[col + 3]);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + rr4;
+                        const long long off = optr[rl];
+                        if (off >= 0) {
+                            float4 v = *reinterpret_cast<const float4*>(stg + (size_t)rl * SP + c4 * 4);
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                            *reinterpret_cast<float4*>(out + off + col) = v;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TCOLS));
+}
+
 static inline int cround(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
@@ -417,6 +624,32 @@ HA2G_API int ha2g_conv_tc(const void* a_hi, const void* a_lo, const void* b_hi, 
     g.RA = CBM + (KH - 1) * g.Wp + (KW - 1);
     const int tiles = (N * g.Hp * g.Wp + CBM - 1) / CBM;
     const int bn = Cd > 64 ? 128 : (Cd > 32 ? 64 : 32);
+    {   // persistent kernel: halo blocks of CPB chunks, double-buffered; falls through to the per-tile kernel if it cannot fit
+        static int persist = -1;
+        if (persist < 0) { const char* e = getenv("HA2G_CONV_PERSIST"); persist = (e != nullptr && e[0] == '0') ? 0 : 1; }
+        ConvTcGeom gp = g;
+        gp.cb = chunks_p > CPB ? CPB : chunks_p;
+        const size_t smem_p = (size_t)4 * gp.cb * gp.RA * 16 + (size_t)CWST * 2 * CSUB * bn * 16 + (size_t)4 * 32 * 36 * 4 + 4 * 32 * 8 + 256;
+        if (persist && chunks_p % gp.cb == 0 && smem_p <= 227 * 1024 && tiles >= 2) {
+            const int nx = ha2g_div_up(Cd, bn);
+            int gy = 148 / nx;
+            if (gy < 1) gy = 1;
+            if (gy > tiles) gy = tiles;
+            dim3 pgrid(nx, gy);
+#define CONV_PLAUNCH(BN_, TF_)                                                                                          \
+            do {                                                                                                      \
+                cudaError_t e_ = cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, TF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p); \
+                if (e_ != cudaSuccess) return (int)e_;                                                                \
+                conv_tc_persist_kernel<BN_, TF_><<<pgrid, CNT, smem_p, stream>>>(reinterpret_cast<const uint4*>(a_hi), reinterpret_cast<const uint4*>(a_lo), \
+                                                                 reinterpret_cast<const uint4*>(b_hi), reinterpret_cast<const uint4*>(b_lo), \
+                                                                 bias, out, gp, tiles);                               \
+            } while (0)
+            if (prec) { if (bn == 128) CONV_PLAUNCH(128, true); else if (bn == 64) CONV_PLAUNCH(64, true); else CONV_PLAUNCH(32, true); }
+            else { if (bn == 128) CONV_PLAUNCH(128, false); else if (bn == 64) CONV_PLAUNCH(64, false); else CONV_PLAUNCH(32, false); }
+#undef CONV_PLAUNCH
+            HA2G_RETURN_LAST();
+        }
+    }
     const size_t smem = (size_t)2 * g.cb * g.RA * 16 + (size_t)CWST * 2 * CSUB * bn * 16 + 256;
     if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
     dim3 grid(ha2g_div_up(Cd, bn), tiles);

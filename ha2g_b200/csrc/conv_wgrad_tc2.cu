@@ -164,14 +164,16 @@ __global__ void __launch_bounds__(WNT, 1) conv_wgrad_tc2_kernel(const uint4* __r
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa_hi = ws32(smem + st * stage_bytes), sa_lo = sa_hi + g.a_stage;
                 const uint32_t sb_hi = sa_lo + g.a_stage, sb_lo = sb_hi + g.b_stage;
+                // descriptors differ only in their start-address field (units of 16 bytes = one pixel row of a chunk plane)
+                const uint64_t da_hi0 = wdesc(sa_hi, 128, WKB * 16), da_lo0 = wdesc(sa_lo, 128, WKB * 16);
+                const uint64_t db_hi0 = wdesc(sb_hi, 128, (uint32_t)(g.RA * 16)), db_lo0 = wdesc(sb_lo, 128, (uint32_t)(g.RA * 16));
                 for (int t = 0; t < g.TG; ++t) {
                     const int toff = all_taps ? (t / g.KW) * g.Wp + (t % g.KW) : t;   // rows from the halo start
                     const uint32_t dcol = tmem_d + (uint32_t)(t * g.NT);
 #pragma unroll
                     for (int ks = 0; ks < WKB / 16; ++ks) {
-                        const uint32_t a_off = (uint32_t)(ks * 16 * 16), b_off = (uint32_t)((toff + ks * 16) * 16);
-                        const uint64_t dah = wdesc(sa_hi + a_off, 128, WKB * 16), dal = wdesc(sa_lo + a_off, 128, WKB * 16);
-                        const uint64_t dbh = wdesc(sb_hi + b_off, 128, (uint32_t)(g.RA * 16)), dbl = wdesc(sb_lo + b_off, 128, (uint32_t)(g.RA * 16));
+                        const uint64_t dah = da_hi0 + (uint64_t)(ks * 16), dal = da_lo0 + (uint64_t)(ks * 16);
+                        const uint64_t dbh = db_hi0 + (uint64_t)(toff + ks * 16), dbl = db_lo0 + (uint64_t)(toff + ks * 16);
                         wmma(dcol, dah, dbh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
                         wmma(dcol, dah, dbl, idesc, 1u);
                         wmma(dcol, dal, dbh, idesc, 1u);
