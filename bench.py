@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--variant", default="expressive", choices=["expressive", "gesture"])
     ap.add_argument("--batch", type=int, default=128, help="clips per GPU")
     ap.add_argument("--epoch", type=int, default=11, help="> loss_warmup (10): full step incl. discriminator")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="clips in the CPU-baseline sample")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="clips in the CPU-baseline sample")
     ap.add_argument("--cpu-timeout", type=float, default=240.0, help="seconds allowed for the CPU-baseline subprocess")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
