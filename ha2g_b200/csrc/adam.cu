@@ -7,6 +7,42 @@
 namespace {
 constexpr int ADAM_CHUNK = 16384;  // elements per CTA-chunk
 
+// One chunk of one tensor.  128-bit accesses when the four arrays are 16-byte aligned (chunk offsets are multiples of
+// 16384 elements, so alignment of the bases is all that matters): 7 x 16 bytes per thread-iteration instead of 7 x 4.
+__device__ __forceinline__ void adam_chunk(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                           float* __restrict__ v, int64_t off, int64_t end, float b1, float b2, float eps,
+                                           float step_size, float bc2_sqrt) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    int64_t i = off;
+    if (vec) {
+        const int64_t n4 = (end - off) >> 2;
+        for (int64_t q = threadIdx.x; q < n4; q += blockDim.x) {
+            const int64_t e = off + (q << 2);
+            const float4 g4 = *reinterpret_cast<const float4*>(g + e);
+            float4 m4 = *reinterpret_cast<const float4*>(m + e), v4 = *reinterpret_cast<const float4*>(v + e);
+            float4 p4 = *reinterpret_cast<const float4*>(p + e);
+#define ADAM_1(c)                                                                  \
+            m4.c = b1 * m4.c + (1.f - b1) * g4.c;                                  \
+            v4.c = b2 * v4.c + (1.f - b2) * g4.c * g4.c;                           \
+            p4.c -= step_size * (m4.c / (sqrtf(v4.c) / bc2_sqrt + eps));
+            ADAM_1(x) ADAM_1(y) ADAM_1(z) ADAM_1(w)
+#undef ADAM_1
+            *reinterpret_cast<float4*>(m + e) = m4;
+            *reinterpret_cast<float4*>(v + e) = v4;
+            *reinterpret_cast<float4*>(p + e) = p4;
+        }
+        i = off + (n4 << 2);
+    }
+    for (i += threadIdx.x; i < end; i += blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+}
+
 // table[k] = {p, g, m, v} device addresses of tensor k;  chunk c -> (tensor chunk_tensor[c], offset chunk_off[c])
 __global__ void __launch_bounds__(256) adam_multi_kernel(const int64_t* __restrict__ table, const int64_t* __restrict__ sizes,
                                                          const int* __restrict__ chunk_tensor,
@@ -20,15 +56,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const int64_t* __restri
     float* __restrict__ v = reinterpret_cast<float*>(table[4 * k + 3]);
     const int64_t n = sizes[k];
     const int64_t end = min(n, off + ADAM_CHUNK);
-    const float step_size = lr / bc1;
-    for (int64_t i = off + threadIdx.x; i < end; i += blockDim.x) {
-        float gi = g[i];
-        float mi = b1 * m[i] + (1.f - b1) * gi;
-        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] -= step_size * (mi / denom);
-    }
+    adam_chunk(p, g, m, v, off, end, b1, b2, eps, lr / bc1, bc2_sqrt);
 }
 // CUDA-graph variant: the step count and the hyper-parameters live in device memory, so one captured launch stays
 // valid for every replay.  state[0] = step count (incremented here); hyper = {lr, b1, b2, eps}; the bias corrections
@@ -52,15 +80,7 @@ __global__ void __launch_bounds__(256) adam_multi_dev_kernel(const int64_t* __re
     float* __restrict__ v = reinterpret_cast<float*>(table[4 * k + 3]);
     const int64_t n = sizes[k];
     const int64_t end = min(n, off + ADAM_CHUNK);
-    const float step_size = lr / bc1;
-    for (int64_t i = off + threadIdx.x; i < end; i += blockDim.x) {
-        float gi = g[i];
-        float mi = b1 * m[i] + (1.f - b1) * gi;
-        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] -= step_size * (mi / denom);
-    }
+    adam_chunk(p, g, m, v, off, end, b1, b2, eps, lr / bc1, bc2_sqrt);
 }
 }  // namespace
 

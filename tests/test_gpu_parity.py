@@ -278,6 +278,11 @@ def test_fused_adam_matches_torch():
     ps = [torch.randn(s) for s in [(7,), (300, 300), (1, 33), (70001,)]]
     ref = [p.clone().requires_grad_(True) for p in ps]
     mine = [p.clone().to(DEV).requires_grad_(True) for p in ps]
+    # a parameter that is NOT 16-byte aligned (a view one element into its storage): the scalar path of the kernel
+    un = torch.randn(1030)
+    ref.append(un[1:].clone().requires_grad_(True))
+    mine.append(un.to(DEV)[1:].detach().requires_grad_(True))
+    assert mine[-1].data_ptr() % 16 == 4
     o_ref = torch.optim.Adam(ref, lr=5e-4, betas=(0.5, 0.999))
     o_mine = torch.optim.Adam(mine, lr=5e-4, betas=(0.5, 0.999))
     for it in range(3):
