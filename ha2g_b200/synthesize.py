@@ -8,6 +8,9 @@ the reference line by line, including its index quirk (the spectrogram window st
 ``spectrogram.shape[0]`` = 128 mel bins where the time length was meant, :84).  What changes is where it runs: the
 mel spectrogram is csrc/mel.cu, the modules are the CUDA modules of ha2g_b200.model, the seed frames stay on the
 device between windows and the cross-fade runs on the device; only the final stacked motion is copied to the host.
+The window body (seed frames -> audio encoder -> L-level cascade, ~600 launches at batch 1) is captured into one CUDA
+graph at the second window and replayed for the rest of the clip (``HA2G_CUDA_GRAPH=0``, or injected randomness, keeps
+every window eager).
 """
 from __future__ import annotations
 
@@ -18,7 +21,11 @@ from typing import List, Sequence
 import numpy as np
 import torch
 
-from . import cascade, mel, ops
+import os
+
+from . import cascade, mel, ops, rng
+
+_GRAPH = os.environ.get("HA2G_CUDA_GRAPH", "1") != "0"
 
 
 def words_in_time_range(word_list: Sequence, start_time: float, end_time: float) -> List:
@@ -95,22 +102,44 @@ def generate_gestures_hierarchy(args, *rest, audio_sr=16000, vid=None, fade_out=
 
     targets = [t.to(dev).float() for t in targets]
     tabs = cascade.device_tables(variant, dev)
-    out_dir_vec = None
+    # static buffers of the window body (also what a captured graph reads and writes)
+    s_spec = torch.empty((1, spectrogram.shape[0], spec_len), device=dev, dtype=torch.float32)
+    s_text = torch.empty((1, n_frames), device=dev, dtype=torch.int64)
+    s_out = torch.zeros((1, n_frames, pose_dim), device=dev, dtype=torch.float32)
+
+    def body(with_seed: bool):
+        if with_seed:  # seed frames: the previous window's last n_pre outputs, per level (:117-125)
+            seed = s_out[:, -n_pre:, :].contiguous()
+            for k in range(L):
+                targets[k][:, 0:n_pre, :] = ops.gather_cols(seed, tabs[k][0])
+        _, _, _, _, linear_blend_feat = audio_encoder(s_spec, vid_t)
+        outs, _ = cascade.run_cascade(variant, gens, targets, s_text, linear_blend_feat, vid_t, n_pre)
+        s_out.copy_(outs[-1])
+
+    use_graph = _GRAPH and not rng.overridden() and len(plan) >= 4 and not torch.cuda.is_current_stream_capturing()
+    graph = None
     chunks: List[torch.Tensor] = []
     for i, (start_time, end_time, spec_start) in enumerate(plan):
-        in_spec = spectrogram[:, spec_start:spec_start + spec_len].unsqueeze(0).contiguous()
+        sl = spectrogram[:, spec_start:spec_start + spec_len]
+        if sl.shape[1] == spec_len:
+            s_spec[0].copy_(sl)
+        else:   # the reference would fail on a short slice too; keep the error explicit
+            raise RuntimeError(f"spectrogram window {i} has {sl.shape[1]} frames, expected {spec_len}")
         a0 = math.floor(start_time / clip_length * len(audio))
         if len(audio) - a0 < audio_sample_length and i == len(plan) - 1:
             end_padding_duration = audio_sample_length - max(0, len(audio) - a0)
-        in_text_padded = torch.from_numpy(place_words(words, start_time, end_time, n_frames, lang_model)).unsqueeze(0).to(dev)
-        if i > 0:  # seed frames: the previous window's last n_pre outputs, per level (:117-125)
-            seed = out_dir_vec[:, -n_pre:, :]
-            for k in range(L):
-                targets[k][:, 0:n_pre, :] = ops.gather_cols(seed, tabs[k][0])
-        _, _, _, _, linear_blend_feat = audio_encoder(in_spec, vid_t)
-        outs, _ = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat, vid_t, n_pre)
-        out_dir_vec = outs[-1]
-        out_seq = out_dir_vec[0].clone()
+        s_text.copy_(torch.from_numpy(place_words(words, start_time, end_time, n_frames, lang_model)).unsqueeze(0))
+        if use_graph and i == 2:   # windows 0 and 1 ran eagerly (both variants of the body are warm): capture the seeded body
+            ops._ensure_workspace()
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body(True)
+        if graph is not None:
+            graph.replay()
+        else:
+            body(i > 0)
+        out_seq = s_out[0].clone()
         if chunks:  # linear cross-fade over the overlapping n_pre frames (:195-203)
             last = chunks[-1][-n_pre:]
             chunks[-1] = chunks[-1][:-n_pre]

@@ -64,3 +64,41 @@ def test_generate_gestures_matches_reference_loop():
         assert out.shape == tuple(g[key].shape), (out.shape, g[key].shape)
         # 2e-3: the CUDA log-mel may differ from the oracle mel by one fp16 ulp in a few bins (tests/test_mel.py)
         assert_close(torch.from_numpy(out), g[key], f"inference {key}", 2e-3)
+
+
+@pytest.mark.gpu
+def test_window_graph_matches_eager():
+    """The CUDA-graph replay of the window body (windows >= 2) must reproduce the eager loop: same clip, same
+    (stateless, cyclic) reparameterisation noise, graph on vs off."""
+    from ha2g_b200 import rng, synthesize
+    dev = "cuda:0"
+    args = make_args("expressive")
+    spk = make_speaker_vocab(5)
+    emb = make_embedding(60, 300, 1).numpy()
+    lang = Vocab("words")
+    for w in ("alpha", "beta", "gamma"):
+        lang.index_word(w)
+    dims = (24, 30, 36, 66, 96, 126)
+    gens = [det_fill(Hierarchical_PoseGenerator(args, d, 60, 300, emb, z_obj=spk), 20 + i).to(dev).train(False)
+            for i, d in enumerate(dims)]
+    A = det_fill(Hierarchical_WavEncoder(args, spk, pose_level=6, nOut=32), 31).to(dev).train(False)
+    audio = make_audio(16000 * 14, 3).numpy()             # 14 s -> 7 windows
+    words = [["alpha", 0.5, 0.9], ["beta", 3.1, 3.4], ["gamma", 7.7, 8.0], ["alpha", 11.0, 11.3]]
+    targets = [randn((1, 34, d), 9, f"t{d}") * 0.1 for d in dims]
+    noise = [randn((1, 16), 10, f"e{i}").to(dev) for i in range(6)]
+    outs = []
+    for graph_on in (False, True):
+        calls = [0]
+
+        def cyc(shape):
+            calls[0] += 1
+            return noise[(calls[0] - 1) % 6]
+        synthesize._GRAPH = graph_on
+        try:
+            with rng.override(randn_fn=cyc, graph_safe=True):
+                outs.append(synthesize.generate_gestures_hierarchy(args, *gens, A, lang, audio, words,
+                                                                   *[t.clone() for t in targets], vid=2))
+        finally:
+            synthesize._GRAPH = True
+    assert outs[0].shape == outs[1].shape and outs[0].shape[0] == 7 * 30 + 4
+    assert_close(torch.from_numpy(outs[1]), torch.from_numpy(outs[0]), "window graph vs eager", 1e-5)
