@@ -140,6 +140,89 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
     }
 }
 
+
+// ---- 128-bit variants of the two apply passes (C % 4 == 0, C <= BN_VEC_MAXC, 16-byte aligned tensors) -----------------
+// Per-channel coefficients are computed once per CTA into shared memory as floats (the scalar kernels redo a double
+// multiply per ELEMENT for the backward coefficients); each thread then streams float4s with its channel quad fixed by a
+// single modulo per float4.
+constexpr int BN_VEC_MAXC = 1024;
+
+__global__ void __launch_bounds__(256) bn_apply_vec_kernel(const float4* __restrict__ x, int64_t n4, int C, int pre_relu,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int post_act, float4* __restrict__ y) {
+    __shared__ float sc[BN_VEC_MAXC], sm[BN_VEC_MAXC], sb[BN_VEC_MAXC];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        sc[c] = invstd[c] * gamma[c];
+        sm[c] = mean[c];
+        sb[c] = beta[c];
+    }
+    __syncthreads();
+    const int C4 = C >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) << 2;
+        float4 v = x[i];
+        if (pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        // (v - mean) * (invstd * gamma) + beta: the mean is subtracted first, as in the scalar kernel (no cancellation)
+        v.x = ha2g_act(fmaf(v.x - sm[c], sc[c], sb[c]), post_act);
+        v.y = ha2g_act(fmaf(v.y - sm[c + 1], sc[c + 1], sb[c + 1]), post_act);
+        v.z = ha2g_act(fmaf(v.z - sm[c + 2], sc[c + 2], sb[c + 2]), post_act);
+        v.w = ha2g_act(fmaf(v.w - sm[c + 3], sc[c + 3], sb[c + 3]), post_act);
+        y[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                                                               const float4* __restrict__ y, int64_t n4, int64_t rows, int C,
+                                                               int pre_relu, int post_act, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const double* __restrict__ sums, float4* __restrict__ dx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    // dx = gamma*invstd*(g - db - xhat*dg)*mask,  xhat = (xv - mean)*invstd  (same evaluation order as the scalar kernel)
+    __shared__ float cA[BN_VEC_MAXC], cM[BN_VEC_MAXC], cI[BN_VEC_MAXC], cDb[BN_VEC_MAXC], cDg[BN_VEC_MAXC];
+    const double invR = 1.0 / (double)rows;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        cA[c] = gamma[c] * invstd[c];
+        cM[c] = mean[c];
+        cI[c] = invstd[c];
+        cDb[c] = (float)(sums[c] * invR);
+        cDg[c] = (float)(sums[C + c] * invR);
+    }
+    __syncthreads();
+    const int C4 = C >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) << 2;
+        float4 g = dy[i];
+        if (post_act) {
+            const float4 yo = y[i];
+            g.x *= ha2g_act_grad_from_out(yo.x, post_act); g.y *= ha2g_act_grad_from_out(yo.y, post_act);
+            g.z *= ha2g_act_grad_from_out(yo.z, post_act); g.w *= ha2g_act_grad_from_out(yo.w, post_act);
+        }
+        const float4 xv = x[i];
+        float4 o;
+#define BN_BWD_1(f, k)                                                            \
+        {                                                                         \
+            float xx = xv.f, m = 1.f;                                             \
+            if (pre_relu) { m = xx > 0.f ? 1.f : 0.f; xx = fmaxf(xx, 0.f); }      \
+            o.f = cA[c + k] * (g.f - cDb[c + k] - (xx - cM[c + k]) * cI[c + k] * cDg[c + k]) * m; \
+        }
+        BN_BWD_1(x, 0) BN_BWD_1(y, 1) BN_BWD_1(z, 2) BN_BWD_1(w, 3)
+#undef BN_BWD_1
+        dx[i] = o;
+    }
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            dbeta[c] += (float)sums[c];
+            dgamma[c] += (float)sums[C + c];
+        }
+    }
+}
+
+static inline bool bn_vec_ok(int C, const void* a, const void* b, const void* c, const void* d) {
+    return C % 4 == 0 && C <= BN_VEC_MAXC &&
+           (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+}
+
 static inline void bn_grid(int64_t rows, int C, dim3& grid, int& rows_per) {
     int gx = ha2g_div_up(C, 32);
     int want_y = ha2g_div_up(148 * 4, gx);
@@ -170,7 +253,12 @@ HA2G_API int ha2g_bn_fwd(const float* x, int64_t rows, int C, int pre_relu, int 
         bn_eval_stats_kernel<<<ha2g_div_up(C, 128), 128, 0, stream>>>(running_mean, running_var, C, eps, mean, invstd);
     }
     const int64_t n = rows * C;
-    bn_apply_kernel<<<ha2g_ew_grid(n), 256, 0, stream>>>(x, n, C, pre_relu, mean, invstd, gamma, beta, post_act, y);
+    if (bn_vec_ok(C, x, y, x, y))
+        bn_apply_vec_kernel<<<ha2g_ew_grid(n / 4, 256, 4), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), n / 4, C, pre_relu,
+                                                                            mean, invstd, gamma, beta, post_act,
+                                                                            reinterpret_cast<float4*>(y));
+    else
+        bn_apply_kernel<<<ha2g_ew_grid(n), 256, 0, stream>>>(x, n, C, pre_relu, mean, invstd, gamma, beta, post_act, y);
     HA2G_RETURN_LAST();
 }
 
@@ -185,7 +273,13 @@ HA2G_API int ha2g_bn_bwd(const float* dy, const float* x, const float* y, int64_
     bn_grid(rows, C, grid, rows_per);
     bn_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd,
                                                            sums_scratch, rows_per);
-    bn_bwd_apply_kernel<<<ha2g_ew_grid(rows * C), 256, 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd,
-                                                                    gamma, sums_scratch, dx, dgamma, dbeta);
+    if (bn_vec_ok(C, dy, x, post_act ? (const void*)y : (const void*)x, dx))
+        bn_bwd_apply_vec_kernel<<<ha2g_ew_grid(rows * C / 4, 256, 4), 256, 0, stream>>>(
+            reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y),
+            rows * C / 4, rows, C, pre_relu, post_act, mean, invstd, gamma, sums_scratch, reinterpret_cast<float4*>(dx), dgamma,
+            dbeta);
+    else
+        bn_bwd_apply_kernel<<<ha2g_ew_grid(rows * C), 256, 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd,
+                                                                        gamma, sums_scratch, dx, dgamma, dbeta);
     HA2G_RETURN_LAST();
 }
