@@ -139,6 +139,91 @@ __global__ void se_bwd_b_kernel(const float* __restrict__ dres /* = dout*(out>0)
     }
 }
 
+
+// ---- 128-bit variants of the SE streaming kernels (C % 4 == 0, 16-byte aligned maps) -------------------------------------
+// Reductions (GAP, ds): a CTA owns a pixel range of one sample; thread = (pixel slot, channel quad) streams float4s, the
+// block reduces over its pixel slots in shared memory and adds ONE partial per channel to the (pre-zeroed) output -- so a
+// 128 x 70 x 32 map is spread over N x splits CTAs instead of N, and every access is 16 bytes.
+constexpr int SE_NT = 256;
+
+template <int MODE>   // 0: gap[n,c] += sum u / HW;   1: g = dout*(out>0) -> dres, ds[n,c] += sum g*u
+__global__ void __launch_bounds__(SE_NT) se_reduce_vec_kernel(const float4* __restrict__ u, const float4* __restrict__ dout,
+                                                              const float4* __restrict__ out, float4* __restrict__ dres,
+                                                              float* __restrict__ acc, int HW, int C, int px_per_cta) {
+    __shared__ float4 sh[SE_NT];
+    const int C4 = C >> 2;
+    const int slots = SE_NT / C4;                 // pixels handled per block iteration (C4 divides 256: C = 8..256, 2^k)
+    const int q = threadIdx.x % C4, slot = threadIdx.x / C4;
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * px_per_cta, p1 = min(HW, p0 + px_per_cta);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slot < slots) {
+        const size_t base = (size_t)n * HW * C4 + q;
+        for (int p = p0 + slot; p < p1; p += slots) {
+            const size_t i = base + (size_t)p * C4;
+            const float4 uv = u[i];
+            if (MODE == 0) {
+                a.x += uv.x; a.y += uv.y; a.z += uv.z; a.w += uv.w;
+            } else {
+                const float4 o = out[i], d = dout[i];
+                float4 g;
+                g.x = o.x > 0.f ? d.x : 0.f; g.y = o.y > 0.f ? d.y : 0.f; g.z = o.z > 0.f ? d.z : 0.f; g.w = o.w > 0.f ? d.w : 0.f;
+                dres[i] = g;
+                a.x = fmaf(g.x, uv.x, a.x); a.y = fmaf(g.y, uv.y, a.y); a.z = fmaf(g.z, uv.z, a.z); a.w = fmaf(g.w, uv.w, a.w);
+            }
+        }
+    }
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    if (slot == 0) {
+        for (int k = 1; k < slots; ++k) {
+            const float4 b = sh[k * C4 + q];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        const float sc = MODE == 0 ? 1.f / (float)HW : 1.f;
+        float* dst = acc + (size_t)n * C + q * 4;
+        atomicAdd(dst, a.x * sc); atomicAdd(dst + 1, a.y * sc); atomicAdd(dst + 2, a.z * sc); atomicAdd(dst + 3, a.w * sc);
+    }
+}
+
+template <int MODE>   // 0: out = relu(u*s + res);   1: du = dres*s + dgap/HW
+__global__ void __launch_bounds__(256) se_stream_vec_kernel(const float4* __restrict__ a, const float* __restrict__ s,
+                                                            const float4* __restrict__ b, const float* __restrict__ dgap,
+                                                            float4* __restrict__ o, int64_t total4, int HW, int C) {
+    const int C4 = C >> 2;
+    const int64_t per_n = (int64_t)HW * C4;
+    const float inv = 1.f / (float)HW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) << 2;
+        const int64_t n = i / per_n;
+        const float4 sv = *reinterpret_cast<const float4*>(s + n * C + c);
+        const float4 av = a[i];
+        float4 r;
+        if (MODE == 0) {
+            const float4 bv = b[i];
+            r.x = fmaxf(fmaf(av.x, sv.x, bv.x), 0.f); r.y = fmaxf(fmaf(av.y, sv.y, bv.y), 0.f);
+            r.z = fmaxf(fmaf(av.z, sv.z, bv.z), 0.f); r.w = fmaxf(fmaf(av.w, sv.w, bv.w), 0.f);
+        } else {
+            const float4 gv = *reinterpret_cast<const float4*>(dgap + n * C + c);
+            r.x = fmaf(av.x, sv.x, gv.x * inv); r.y = fmaf(av.y, sv.y, gv.y * inv);
+            r.z = fmaf(av.z, sv.z, gv.z * inv); r.w = fmaf(av.w, sv.w, gv.w * inv);
+        }
+        o[i] = r;
+    }
+}
+
+static inline bool se_vec_ok(int C, const void* a, const void* b, const void* c, const void* d) {
+    return C >= 8 && C <= 256 && (C & (C - 1)) == 0 &&
+           (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+}
+static inline void se_reduce_grid(int N, int HW, int& splits, int& px) {
+    splits = (148 * 4 + N - 1) / N;
+    if (splits > (HW + 63) / 64) splits = (HW + 63) / 64;
+    if (splits < 1) splits = 1;
+    px = (HW + splits - 1) / splits;
+    splits = (HW + px - 1) / px;
+}
+
 // ---- index remaps -------------------------------------------------------------------------------------
 // PixelShuffle(r), NHWC:  out[n, h*r+i, w*r+j, c] = in[n, h, w, c*r*r + i*r + j].   inverse: swap roles.
 __global__ void pixel_shuffle_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t N, int H, int W, int Cout,
@@ -240,10 +325,25 @@ HA2G_API int ha2g_se_fwd(const float* u, const float* res, const float* w1, cons
                          const float* b2, float* gap, float* h, float* s, float* out, int N, int HW, int C, int R,
                          cudaStream_t stream) {
     if (C > 256 || R > 32) return (int)cudaErrorInvalidValue;
-    se_gap_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(u, gap, HW, C);
+    const bool vec = se_vec_ok(C, u, res, out, s);
+    if (vec) {
+        cudaError_t ce = cudaMemsetAsync(gap, 0, sizeof(float) * (size_t)N * C, stream);
+        if (ce != cudaSuccess) return (int)ce;
+        int splits, px;
+        se_reduce_grid(N, HW, splits, px);
+        se_reduce_vec_kernel<0><<<dim3(splits, N), SE_NT, 0, stream>>>(reinterpret_cast<const float4*>(u), nullptr, nullptr, nullptr,
+                                                                      gap, HW, C, px);
+    } else {
+        se_gap_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(u, gap, HW, C);
+    }
     se_fc_fwd_kernel<<<N, 256, 0, stream>>>(gap, w1, b1, w2, b2, h, s, C, R);
     int64_t total = (int64_t)N * HW * C;
-    se_apply_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(u, s, res, out, total, HW, C);
+    if (vec)
+        se_stream_vec_kernel<0><<<ha2g_ew_grid(total / 4, 256, 4), 256, 0, stream>>>(reinterpret_cast<const float4*>(u), s,
+                                                                                    reinterpret_cast<const float4*>(res), nullptr,
+                                                                                    reinterpret_cast<float4*>(out), total / 4, HW, C);
+    else
+        se_apply_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(u, s, res, out, total, HW, C);
     HA2G_RETURN_LAST();
 }
 // SE tail backward.  dres (= dout*(out>0)) and du are outputs [N,HW,C]; dw1,db1,dw2,db2 ACCUMULATED; ds,dgap scratch [N,C].
@@ -252,10 +352,26 @@ HA2G_API int ha2g_se_bwd(const float* dout, const float* out, const float* u, co
                          float* dw1, float* db1, float* dw2, float* db2, int N, int HW, int C, int R,
                          cudaStream_t stream) {
     if (C > 256 || R > 32) return (int)cudaErrorInvalidValue;
-    se_bwd_a_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(dout, out, u, dres, ds, HW, C);
+    const bool vec = se_vec_ok(C, dout, out, u, dres) && se_vec_ok(C, du, s, dgap, du);
+    if (vec) {
+        cudaError_t ce = cudaMemsetAsync(ds, 0, sizeof(float) * (size_t)N * C, stream);
+        if (ce != cudaSuccess) return (int)ce;
+        int splits, px;
+        se_reduce_grid(N, HW, splits, px);
+        se_reduce_vec_kernel<1><<<dim3(splits, N), SE_NT, 0, stream>>>(reinterpret_cast<const float4*>(u),
+                                                                      reinterpret_cast<const float4*>(dout),
+                                                                      reinterpret_cast<const float4*>(out),
+                                                                      reinterpret_cast<float4*>(dres), ds, HW, C, px);
+    } else {
+        se_bwd_a_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(dout, out, u, dres, ds, HW, C);
+    }
     se_fc_bwd_kernel<<<N, 256, 0, stream>>>(ds, s, h, gap, w1, w2, dw1, db1, dw2, db2, dgap, C, R);
     int64_t total = (int64_t)N * HW * C;
-    se_bwd_b_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(dres, s, dgap, du, total, HW, C);
+    if (vec)
+        se_stream_vec_kernel<1><<<ha2g_ew_grid(total / 4, 256, 4), 256, 0, stream>>>(reinterpret_cast<const float4*>(dres), s, nullptr,
+                                                                                    dgap, reinterpret_cast<float4*>(du), total / 4, HW, C);
+    else
+        se_bwd_b_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(dres, s, dgap, du, total, HW, C);
     HA2G_RETURN_LAST();
 }
 // nn.PixelShuffle(r) on NHWC: src [N,H,W,Cout*r*r] -> dst [N,H*r,W*r,Cout]  (inverse != 0: the other way)
