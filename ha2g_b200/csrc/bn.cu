@@ -223,6 +223,74 @@ static inline bool bn_vec_ok(int C, const void* a, const void* b, const void* c,
            (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
 }
 
+
+// 128-bit column reductions: a CTA owns a row range; thread = (row slot, channel quad).  MODE 0: sums of f(x), f(x)^2
+// (forward statistics);  MODE 1: sums of g and g*xhat (backward).  Partial sums are kept in float for 64 rows at a time
+// and flushed into double accumulators, exactly like the scalar kernels.
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_reduce_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                                            const float4* __restrict__ y, int64_t rows, int C, int pre_relu,
+                                                            int post_act, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, double* __restrict__ sums,
+                                                            int rows_per_cta) {
+    __shared__ double sh[2][256][4];
+    const int C4 = C >> 2;
+    const int slots = 256 / C4;
+    const int q = threadIdx.x % C4, slot = threadIdx.x / C4;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + (int64_t)rows_per_cta);
+    double ds[4] = {0.0, 0.0, 0.0, 0.0}, dq[4] = {0.0, 0.0, 0.0, 0.0};
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu;
+    if (MODE == 1) { mu = *reinterpret_cast<const float4*>(mean + q * 4); is = *reinterpret_cast<const float4*>(invstd + q * 4); }
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, qq[4] = {0.f, 0.f, 0.f, 0.f};
+    int cnt = 0;
+    for (int64_t r = r0 + slot; r < r1; r += slots) {
+        const int64_t i = r * C4 + q;
+        float4 v = x[i];
+        if (pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (MODE == 0) {
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            qq[0] += v.x * v.x; qq[1] += v.y * v.y; qq[2] += v.z * v.z; qq[3] += v.w * v.w;
+        } else {
+            float4 g = dy[i];
+            if (post_act) {
+                const float4 yo = y[i];
+                g.x *= ha2g_act_grad_from_out(yo.x, post_act); g.y *= ha2g_act_grad_from_out(yo.y, post_act);
+                g.z *= ha2g_act_grad_from_out(yo.z, post_act); g.w *= ha2g_act_grad_from_out(yo.w, post_act);
+            }
+            s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+            qq[0] += g.x * (v.x - mu.x) * is.x; qq[1] += g.y * (v.y - mu.y) * is.y;
+            qq[2] += g.z * (v.z - mu.z) * is.z; qq[3] += g.w * (v.w - mu.w) * is.w;
+        }
+        if (++cnt == 64) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { ds[k] += s[k]; dq[k] += qq[k]; s[k] = 0.f; qq[k] = 0.f; }
+            cnt = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sh[0][threadIdx.x][k] = ds[k] + s[k]; sh[1][threadIdx.x][k] = dq[k] + qq[k]; }
+    __syncthreads();
+    if (slot == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double a = 0.0, b = 0.0;
+            for (int j = 0; j < slots; ++j) { a += sh[0][j * C4 + q][k]; b += sh[1][j * C4 + q][k]; }
+            atomicAdd(sums + q * 4 + k, a);
+            atomicAdd(sums + C + q * 4 + k, b);
+        }
+    }
+}
+static inline bool bn_red_vec_ok(int C, const void* a, const void* b, const void* c) {
+    return C >= 8 && C <= 1024 && (C & (C - 1)) == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+}
+static inline void bn_red_grid(int64_t rows, int& ctas, int& rows_per) {
+    int64_t want = 148 * 4;
+    int64_t rp = (rows + want - 1) / want;
+    if (rp < 64) rp = 64;
+    rows_per = (int)rp;
+    ctas = (int)((rows + rp - 1) / rp);
+}
+
 static inline void bn_grid(int64_t rows, int C, dim3& grid, int& rows_per) {
     int gx = ha2g_div_up(C, 32);
     int want_y = ha2g_div_up(148 * 4, gx);
@@ -245,8 +313,15 @@ HA2G_API int ha2g_bn_fwd(const float* x, int64_t rows, int C, int pre_relu, int 
         cudaError_t ce = cudaMemsetAsync(sums_scratch, 0, sizeof(double) * 2 * C, stream);
         if (ce != cudaSuccess) return (int)ce;
         dim3 grid; int rows_per;
-        bn_grid(rows, C, grid, rows_per);
-        bn_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, C, pre_relu, sums_scratch, rows_per);
+        if (bn_red_vec_ok(C, x, x, x)) {
+            int ctas;
+            bn_red_grid(rows, ctas, rows_per);
+            bn_reduce_vec_kernel<0><<<ctas, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), nullptr, nullptr, rows, C, pre_relu,
+                                                              0, nullptr, nullptr, sums_scratch, rows_per);
+        } else {
+            bn_grid(rows, C, grid, rows_per);
+            bn_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, C, pre_relu, sums_scratch, rows_per);
+        }
         bn_finalize_kernel<<<ha2g_div_up(C, 128), 128, 0, stream>>>(sums_scratch, rows, C, eps, momentum, mean, invstd,
                                                                     running_mean, running_var);
     } else {
@@ -270,9 +345,17 @@ HA2G_API int ha2g_bn_bwd(const float* dy, const float* x, const float* y, int64_
     cudaError_t ce = cudaMemsetAsync(sums_scratch, 0, sizeof(double) * 2 * C, stream);
     if (ce != cudaSuccess) return (int)ce;
     dim3 grid; int rows_per;
-    bn_grid(rows, C, grid, rows_per);
-    bn_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd,
-                                                           sums_scratch, rows_per);
+    if (bn_red_vec_ok(C, x, dy, post_act ? (const void*)y : (const void*)x) && bn_red_vec_ok(C, mean, invstd, x)) {
+        int ctas;
+        bn_red_grid(rows, ctas, rows_per);
+        bn_reduce_vec_kernel<1><<<ctas, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy),
+                                                          reinterpret_cast<const float4*>(y), rows, C, pre_relu, post_act, mean,
+                                                          invstd, sums_scratch, rows_per);
+    } else {
+        bn_grid(rows, C, grid, rows_per);
+        bn_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd,
+                                                               sums_scratch, rows_per);
+    }
     if (bn_vec_ok(C, dy, x, post_act ? (const void*)y : (const void*)x, dx))
         bn_bwd_apply_vec_kernel<<<ha2g_ew_grid(rows * C / 4, 256, 4), 256, 0, stream>>>(
             reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y),
