@@ -167,6 +167,35 @@ __global__ void shift_concat_fwd_kernel(const float* __restrict__ x, float* __re
         out[i] = v;
     }
 }
+// 128-bit variants (C % 4 == 0, 16-byte aligned tensors): one float4 per thread-iteration, index math per float4
+__global__ void shift_concat_fwd_vec_kernel(const float4* __restrict__ x, float4* __restrict__ out, int64_t B, int T, int C4,
+                                            int d) {
+    const int64_t n = B * T * 2 * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c2 = (int)(i % (2 * C4));
+        const int64_t bt = i / (2 * C4);
+        const int t = (int)(bt % T);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c2 < C4) { if (t >= d) v = x[(bt - d) * C4 + c2]; }
+        else v = x[bt * C4 + (c2 - C4)];
+        out[i] = v;
+    }
+}
+__global__ void shift_concat_bwd_vec_kernel(const float4* __restrict__ dout, float4* __restrict__ dx, int64_t B, int T,
+                                            int C4, int d) {
+    const int64_t n = B * T * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const int64_t bt = i / C4;
+        const int t = (int)(bt % T);
+        float4 v = dout[bt * 2 * C4 + C4 + c];
+        if (t + d < T) {
+            const float4 w = dout[(bt + d) * 2 * C4 + c];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        dx[i] = v;
+    }
+}
 // dx[b,t] = dout[b,t][C:2C] + (t+d < T ? dout[b,t+d][0:C] : 0)
 __global__ void shift_concat_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int64_t B, int T, int C,
                                         int d) {
@@ -294,9 +323,23 @@ HA2G_API int ha2g_tcn_weight_bwd(const float* dwcat, const float* g, const float
 }
 // causal dilated k=2 conv input staging (tcn.py:19-21 padding + Chomp1d)
 HA2G_API int ha2g_shift_concat_fwd(const float* x, float* out, int64_t B, int T, int C, int d, cudaStream_t stream) {
+    if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const int64_t n4 = B * T * 2 * (C / 4);
+        if (n4 <= 0) return 0;
+        shift_concat_fwd_vec_kernel<<<ha2g_ew_grid(n4, 256, 2), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                                               reinterpret_cast<float4*>(out), B, T, C / 4, d);
+        HA2G_RETURN_LAST();
+    }
     EW_LAUNCH(shift_concat_fwd_kernel, B * T * 2 * C, x, out, B, T, C, d);
 }
 HA2G_API int ha2g_shift_concat_bwd(const float* dout, float* dx, int64_t B, int T, int C, int d, cudaStream_t stream) {
+    if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+        const int64_t n4 = B * T * (C / 4);
+        if (n4 <= 0) return 0;
+        shift_concat_bwd_vec_kernel<<<ha2g_ew_grid(n4, 256, 2), 256, 0, stream>>>(reinterpret_cast<const float4*>(dout),
+                                                                               reinterpret_cast<float4*>(dx), B, T, C / 4, d);
+        HA2G_RETURN_LAST();
+    }
     EW_LAUNCH(shift_concat_bwd_kernel, B * T * C, dout, dx, B, T, C, d);
 }
 HA2G_API int ha2g_pre_seq_fwd(const float* target_k, const float* prev_out, int dp, const int* slot_src, float* pre,
