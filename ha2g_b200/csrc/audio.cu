@@ -89,11 +89,12 @@ __global__ void se_bwd_a_kernel(const float* __restrict__ dout, const float* __r
     }
 }
 
-// per sample FC backward; weight/bias grads accumulated with atomics.  grid N, block C
+// per sample FC backward: dgap, plus the pre-activation gradients dz2 [N,C] / dz1 [N,R] for the weight-gradient pass
+// (se_fc_wgrad_kernel sums them over the samples in index order: no atomics).  grid N, block C
 __global__ void se_fc_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ sbuf, const float* __restrict__ hbuf,
                                  const float* __restrict__ gap, const float* __restrict__ w1, const float* __restrict__ w2,
-                                 float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
-                                 float* __restrict__ db2, float* __restrict__ dgap, int C, int R) {
+                                 float* __restrict__ dz2_out, float* __restrict__ dz1_out, float* __restrict__ dgap, int C,
+                                 int R) {
     __shared__ float dz2[256];
     __shared__ float dz1[32];
     __shared__ float h[32];
@@ -106,26 +107,55 @@ __global__ void se_fc_bwd_kernel(const float* __restrict__ ds, const float* __re
         g[t] = gap[(size_t)n * C + t];
     }
     __syncthreads();
-    if (t < C) {
-        atomicAdd(db2 + t, dz2[t]);
-        for (int r = 0; r < R; ++r) atomicAdd(dw2 + t * R + r, dz2[t] * h[r]);
-    }
+    if (t < C) dz2_out[(size_t)n * C + t] = dz2[t];
     if (t < R) {
         float a = 0.f;
         for (int c = 0; c < C; ++c) a = fmaf(w2[c * R + t], dz2[c], a);
         a = h[t] > 0.f ? a : 0.f;
         dz1[t] = a;
-        atomicAdd(db1 + t, a);
+        dz1_out[(size_t)n * R + t] = a;
     }
     __syncthreads();
     if (t < C) {
         float a = 0.f;
-        for (int r = 0; r < R; ++r) {
-            a = fmaf(w1[r * C + t], dz1[r], a);
-            atomicAdd(dw1 + r * C + t, dz1[r] * g[t]);
-        }
+        for (int r = 0; r < R; ++r) a = fmaf(w1[r * C + t], dz1[r], a);
         dgap[(size_t)n * C + t] = a;
     }
+}
+// dw2[c][r] += sum_n dz2[n,c] h[n,r];  db2[c] += sum_n dz2[n,c];  dw1[r][c] += sum_n dz1[n,r] gap[n,c];  db1[r] += sum_n dz1[n,r]
+// one thread per (c, r) pair (+ the bias columns), samples summed in index order
+__global__ void se_fc_wgrad_kernel(const float* __restrict__ dz2, const float* __restrict__ dz1, const float* __restrict__ hbuf,
+                                   const float* __restrict__ gap, float* __restrict__ dw1, float* __restrict__ db1,
+                                   float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= C * (R + 1)) return;
+    const int c = e / (R + 1), r = e % (R + 1);
+    if (r == R) {
+        float a = 0.f;
+        for (int n = 0; n < N; ++n) a += dz2[(size_t)n * C + c];
+        db2[c] += a;
+        if (c < R) {
+            float b = 0.f;
+            for (int n = 0; n < N; ++n) b += dz1[(size_t)n * R + c];
+            db1[c] += b;
+        }
+    } else {
+        float a = 0.f, b = 0.f;
+        for (int n = 0; n < N; ++n) {
+            a = fmaf(dz2[(size_t)n * C + c], hbuf[(size_t)n * R + r], a);
+            b = fmaf(dz1[(size_t)n * R + r], gap[(size_t)n * C + c], b);
+        }
+        dw2[c * R + r] += a;
+        dw1[r * C + c] += b;
+    }
+}
+// acc[i] = scale * (part[0][i] + part[1][i] + ...) in index order
+__global__ void se_combine_kernel(const float* __restrict__ part, int nparts, int n, float scale, float* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = 0.f;
+    for (int p = 0; p < nparts; ++p) t += part[(size_t)p * n + i];
+    acc[i] = t * scale;
 }
 
 // du = (dout * (out>0)) * s[n,c] + dgap[n,c] / HW
@@ -142,11 +172,12 @@ __global__ void se_bwd_b_kernel(const float* __restrict__ dres /* = dout*(out>0)
 
 // ---- 128-bit variants of the SE streaming kernels (C % 4 == 0, 16-byte aligned maps) -------------------------------------
 // Reductions (GAP, ds): a CTA owns a pixel range of one sample; thread = (pixel slot, channel quad) streams float4s, the
-// block reduces over its pixel slots in shared memory and adds ONE partial per channel to the (pre-zeroed) output -- so a
-// 128 x 70 x 32 map is spread over N x splits CTAs instead of N, and every access is 16 bytes.
+// block reduces over its pixel slots in shared memory and stores ONE partial per channel into its own plane
+// acc[split][n][c] (se_combine_kernel adds the planes in order) -- so a 128 x 70 x 32 map is spread over N x splits CTAs
+// instead of N, every access is 16 bytes, and the result does not depend on CTA scheduling.
 constexpr int SE_NT = 256;
 
-template <int MODE>   // 0: gap[n,c] += sum u / HW;   1: g = dout*(out>0) -> dres, ds[n,c] += sum g*u
+template <int MODE>   // 0: partial sums of u;   1: g = dout*(out>0) -> dres, partial sums of g*u
 __global__ void __launch_bounds__(SE_NT) se_reduce_vec_kernel(const float4* __restrict__ u, const float4* __restrict__ dout,
                                                               const float4* __restrict__ out, float4* __restrict__ dres,
                                                               float* __restrict__ acc, int HW, int C, int px_per_cta) {
@@ -180,9 +211,7 @@ __global__ void __launch_bounds__(SE_NT) se_reduce_vec_kernel(const float4* __re
             const float4 b = sh[k * C4 + q];
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
-        const float sc = MODE == 0 ? 1.f / (float)HW : 1.f;
-        float* dst = acc + (size_t)n * C + q * 4;
-        atomicAdd(dst, a.x * sc); atomicAdd(dst + 1, a.y * sc); atomicAdd(dst + 2, a.z * sc); atomicAdd(dst + 3, a.w * sc);
+        *reinterpret_cast<float4*>(acc + ((size_t)blockIdx.x * gridDim.y + n) * C + q * 4) = a;
     }
 }
 
@@ -327,12 +356,13 @@ HA2G_API int ha2g_se_fwd(const float* u, const float* res, const float* w1, cons
     if (C > 256 || R > 32) return (int)cudaErrorInvalidValue;
     const bool vec = se_vec_ok(C, u, res, out, s);
     if (vec) {
-        cudaError_t ce = cudaMemsetAsync(gap, 0, sizeof(float) * (size_t)N * C, stream);
-        if (ce != cudaSuccess) return (int)ce;
         int splits, px;
         se_reduce_grid(N, HW, splits, px);
+        float* part = reinterpret_cast<float*>(ha2g_ws((size_t)splits * N * C * sizeof(float)));
+        if (part == nullptr) return (int)cudaErrorMemoryAllocation;
         se_reduce_vec_kernel<0><<<dim3(splits, N), SE_NT, 0, stream>>>(reinterpret_cast<const float4*>(u), nullptr, nullptr, nullptr,
-                                                                      gap, HW, C, px);
+                                                                      part, HW, C, px);
+        se_combine_kernel<<<ha2g_div_up(N * C, 256), 256, 0, stream>>>(part, splits, N * C, 1.f / (float)HW, gap);
     } else {
         se_gap_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(u, gap, HW, C);
     }
@@ -354,18 +384,23 @@ HA2G_API int ha2g_se_bwd(const float* dout, const float* out, const float* u, co
     if (C > 256 || R > 32) return (int)cudaErrorInvalidValue;
     const bool vec = se_vec_ok(C, dout, out, u, dres) && se_vec_ok(C, du, s, dgap, du);
     if (vec) {
-        cudaError_t ce = cudaMemsetAsync(ds, 0, sizeof(float) * (size_t)N * C, stream);
-        if (ce != cudaSuccess) return (int)ce;
         int splits, px;
         se_reduce_grid(N, HW, splits, px);
+        float* part = reinterpret_cast<float*>(ha2g_ws((size_t)splits * N * C * sizeof(float)));
+        if (part == nullptr) return (int)cudaErrorMemoryAllocation;
         se_reduce_vec_kernel<1><<<dim3(splits, N), SE_NT, 0, stream>>>(reinterpret_cast<const float4*>(u),
                                                                       reinterpret_cast<const float4*>(dout),
                                                                       reinterpret_cast<const float4*>(out),
-                                                                      reinterpret_cast<float4*>(dres), ds, HW, C, px);
+                                                                      reinterpret_cast<float4*>(dres), part, HW, C, px);
+        se_combine_kernel<<<ha2g_div_up(N * C, 256), 256, 0, stream>>>(part, splits, N * C, 1.f, ds);
     } else {
         se_bwd_a_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(dout, out, u, dres, ds, HW, C);
     }
-    se_fc_bwd_kernel<<<N, 256, 0, stream>>>(ds, s, h, gap, w1, w2, dw1, db1, dw2, db2, dgap, C, R);
+    float* dz2 = reinterpret_cast<float*>(ha2g_ws((size_t)N * (C + R) * sizeof(float)));
+    if (dz2 == nullptr) return (int)cudaErrorMemoryAllocation;
+    float* dz1 = dz2 + (size_t)N * C;
+    se_fc_bwd_kernel<<<N, 256, 0, stream>>>(ds, s, h, gap, w1, w2, dz2, dz1, dgap, C, R);
+    se_fc_wgrad_kernel<<<ha2g_div_up(C * (R + 1), 128), 128, 0, stream>>>(dz2, dz1, h, gap, dw1, db1, dw2, db2, N, C, R);
     int64_t total = (int64_t)N * HW * C;
     if (vec)
         se_stream_vec_kernel<1><<<ha2g_ew_grid(total / 4, 256, 4), 256, 0, stream>>>(reinterpret_cast<const float4*>(dres), s, nullptr,

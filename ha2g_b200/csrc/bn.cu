@@ -34,9 +34,19 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a += sh[0][i][threadIdx.x]; b += sh[1][i][threadIdx.x]; }
-        atomicAdd(sums + c, a);
-        atomicAdd(sums + C + c, b);
+        double* dst = sums + (size_t)blockIdx.y * 2 * C;   // this row chunk's partial [2][C]
+        dst[c] = a;
+        dst[C + c] = b;
     }
+}
+
+// sums[2C] = sum over the row-chunk partials, in chunk order (deterministic: no atomics anywhere in the reduction)
+__global__ void bn_combine_kernel(const double* __restrict__ part, int nparts, int C2, double* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C2) return;
+    double t = 0.0;
+    for (int p = 0; p < nparts; ++p) t += part[(size_t)p * C2 + i];
+    sums[i] = t;
 }
 
 // mean / invstd from the sums; running-stat update (momentum, unbiased var) as nn.BatchNorm does in train mode
@@ -108,8 +118,9 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* 
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a += sh[0][i][threadIdx.x]; b += sh[1][i][threadIdx.x]; }
-        atomicAdd(sums + c, a);
-        atomicAdd(sums + C + c, b);
+        double* dst = sums + (size_t)blockIdx.y * 2 * C;
+        dst[c] = a;
+        dst[C + c] = b;
     }
 }
 
@@ -275,8 +286,9 @@ __global__ void __launch_bounds__(256) bn_reduce_vec_kernel(const float4* __rest
         for (int k = 0; k < 4; ++k) {
             double a = 0.0, b = 0.0;
             for (int j = 0; j < slots; ++j) { a += sh[0][j * C4 + q][k]; b += sh[1][j * C4 + q][k]; }
-            atomicAdd(sums + q * 4 + k, a);
-            atomicAdd(sums + C + q * 4 + k, b);
+            double* dst = sums + (size_t)blockIdx.x * 2 * C;
+            dst[q * 4 + k] = a;
+            dst[C + q * 4 + k] = b;
         }
     }
 }
@@ -310,18 +322,18 @@ HA2G_API int ha2g_bn_fwd(const float* x, int64_t rows, int C, int pre_relu, int 
                          float momentum, float* mean, float* invstd, double* sums_scratch, float* y, cudaStream_t stream) {
     if (rows <= 0) return 0;
     if (training) {
-        cudaError_t ce = cudaMemsetAsync(sums_scratch, 0, sizeof(double) * 2 * C, stream);
-        if (ce != cudaSuccess) return (int)ce;
-        dim3 grid; int rows_per;
-        if (bn_red_vec_ok(C, x, x, x)) {
-            int ctas;
-            bn_red_grid(rows, ctas, rows_per);
-            bn_reduce_vec_kernel<0><<<ctas, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), nullptr, nullptr, rows, C, pre_relu,
-                                                              0, nullptr, nullptr, sums_scratch, rows_per);
-        } else {
-            bn_grid(rows, C, grid, rows_per);
-            bn_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, C, pre_relu, sums_scratch, rows_per);
-        }
+        dim3 grid; int rows_per, nparts;
+        const bool vec = bn_red_vec_ok(C, x, x, x);
+        if (vec) bn_red_grid(rows, nparts, rows_per);
+        else { bn_grid(rows, C, grid, rows_per); nparts = (int)grid.y; }
+        double* part = reinterpret_cast<double*>(ha2g_ws((size_t)nparts * 2 * C * sizeof(double)));
+        if (part == nullptr) return (int)cudaErrorMemoryAllocation;
+        if (vec)
+            bn_reduce_vec_kernel<0><<<nparts, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), nullptr, nullptr, rows, C, pre_relu,
+                                                                0, nullptr, nullptr, part, rows_per);
+        else
+            bn_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, C, pre_relu, part, rows_per);
+        bn_combine_kernel<<<ha2g_div_up(2 * C, 128), 128, 0, stream>>>(part, nparts, 2 * C, sums_scratch);
         bn_finalize_kernel<<<ha2g_div_up(C, 128), 128, 0, stream>>>(sums_scratch, rows, C, eps, momentum, mean, invstd,
                                                                     running_mean, running_var);
     } else {
@@ -342,20 +354,19 @@ HA2G_API int ha2g_bn_bwd(const float* dy, const float* x, const float* y, int64_
                          const float* gamma, const float* mean, const float* invstd, double* sums_scratch, float* dx,
                          float* dgamma, float* dbeta, cudaStream_t stream) {
     if (rows <= 0) return 0;
-    cudaError_t ce = cudaMemsetAsync(sums_scratch, 0, sizeof(double) * 2 * C, stream);
-    if (ce != cudaSuccess) return (int)ce;
-    dim3 grid; int rows_per;
-    if (bn_red_vec_ok(C, x, dy, post_act ? (const void*)y : (const void*)x) && bn_red_vec_ok(C, mean, invstd, x)) {
-        int ctas;
-        bn_red_grid(rows, ctas, rows_per);
-        bn_reduce_vec_kernel<1><<<ctas, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy),
-                                                          reinterpret_cast<const float4*>(y), rows, C, pre_relu, post_act, mean,
-                                                          invstd, sums_scratch, rows_per);
-    } else {
-        bn_grid(rows, C, grid, rows_per);
-        bn_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd,
-                                                               sums_scratch, rows_per);
-    }
+    dim3 grid; int rows_per, nparts;
+    const bool rvec = bn_red_vec_ok(C, x, dy, post_act ? (const void*)y : (const void*)x) && bn_red_vec_ok(C, mean, invstd, x);
+    if (rvec) bn_red_grid(rows, nparts, rows_per);
+    else { bn_grid(rows, C, grid, rows_per); nparts = (int)grid.y; }
+    double* part = reinterpret_cast<double*>(ha2g_ws((size_t)nparts * 2 * C * sizeof(double)));
+    if (part == nullptr) return (int)cudaErrorMemoryAllocation;
+    if (rvec)
+        bn_reduce_vec_kernel<1><<<nparts, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy),
+                                                            reinterpret_cast<const float4*>(y), rows, C, pre_relu, post_act, mean,
+                                                            invstd, part, rows_per);
+    else
+        bn_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd, part, rows_per);
+    bn_combine_kernel<<<ha2g_div_up(2 * C, 128), 128, 0, stream>>>(part, nparts, 2 * C, sums_scratch);
     if (bn_vec_ok(C, dy, x, post_act ? (const void*)y : (const void*)x, dx))
         bn_bwd_apply_vec_kernel<<<ha2g_ew_grid(rows * C / 4, 256, 4), 256, 0, stream>>>(
             reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y),

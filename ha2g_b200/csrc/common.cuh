@@ -9,6 +9,16 @@
 #define HA2G_RETURN_LAST() \
     do { cudaError_t e__ = cudaPeekAtLastError(); return (int)e__; } while (0)
 
+// The scratch arena registered with ha2g_set_workspace (gemm_tc2.cu): nullptr when it is missing or smaller than `need`.
+// Launchers on one stream may all use it from offset 0 (stream order keeps their uses apart).
+unsigned char* ha2g_ws(size_t need_bytes);
+// The top quarter of the same arena, reserved for the partial tiles of deterministic split-K reductions (so that a GEMM's
+// packed operands at the bottom and its partials never overlap).
+unsigned char* ha2g_ws_top(size_t need_bytes);
+// C[m][n] = (accumulate ? C[m][n] : 0) + bias[n] + part[0][m][n] + part[1][m][n] + ...  (index order: deterministic)
+int ha2g_splitk_reduce(const float* part, int nz, int M, int N, float* C, int ldc, const float* bias, int accumulate,
+                       cudaStream_t stream);
+
 static inline int ha2g_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // Grid sizing for grid-stride element-wise kernels: a multiple of the SM count (148 on B200),

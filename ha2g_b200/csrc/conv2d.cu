@@ -7,7 +7,7 @@
 //     wb [KH*KW*Cout, Cin ]   row (r*KW+s)*Cout + co    (dgrad GEMM-B layout)
 // GEMM view:  fwd   : [N*Ho*Wo, KH*KW*Cin ] x wf -> y      (A gathered on the fly, never materialised)
 //             dgrad : [N*H*W  , KH*KW*Cout] x wb -> dx     (A = dy gathered through the transposed map)
-//             wgrad : A^T [KH*KW*Cin, N*Ho*Wo] x dy -> dwf (split over pixels, atomicAdd)
+//             wgrad : A^T [KH*KW*Cin, N*Ho*Wo] x dy -> dwf (split over pixels, ordered reduction of partial planes)
 // Requirements of the generic kernels: Cin % 16 == 0 (fwd, wgrad), Cout % 16 == 0 (dgrad).  The
 // 1-channel stem has its own direct kernels.
 #include "common.cuh"
@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(CNT) conv2d_igemm_kernel(const float* __restri
 }
 
 // ---- wgrad ---------------------------------------------------------------------------------------
-// dwf[(r,s,ci), co] += sum_{pixels in this split} x_gather[p,(r,s,ci)] * dy[p,co]
+// part[split][(r,s,ci), co] = sum_{pixels in this split} x_gather[p,(r,s,ci)] * dy[p,co]   (`dwf` points at the partial
+// planes, one per pixel split; ha2g_splitk_reduce adds them in order: deterministic)
 template <int BN>
 __global__ void __launch_bounds__(CNT) conv2d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                            float* __restrict__ dwf, ConvGeom g, int64_t pix_per_split) {
@@ -217,10 +218,11 @@ __global__ void __launch_bounds__(CNT) conv2d_wgrad_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    if (p_beg >= p_end) return;
     int buf = 0;
-    load(p_beg);
-    store(0);
+    if (p_beg < p_end) {
+        load(p_beg);
+        store(0);
+    }
     __syncthreads();
     for (int64_t p0 = p_beg; p0 < p_end; p0 += CBK) {
         const bool has_next = p0 + CBK < p_end;
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(CNT) conv2d_wgrad_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int gn = n0 + tx * 4 + j;
-            if (gn < g.Cout) atomicAdd(dwf + (int64_t)kd * g.Cout + gn, acc[i][j]);
+            if (gn < g.Cout) dwf[((int64_t)blockIdx.z * Kd + kd) * g.Cout + gn] = acc[i][j];
         }
     }
 }
@@ -300,9 +302,10 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
         y[e] = acc;
     }
 }
-// dw[co,0,r,s] += sum_pixels x[..]*dy[p,co];  db[co] += sum dy.   One CTA handles a pixel range; Cout <= 32.
-__global__ void stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
-                                  float* __restrict__ db, int N, int H, int W, int Cout, int64_t pix_per_cta) {
+// part[cta][i][co] (i < 9: dw tap, i == 9: db) = sums over this CTA's pixel range; reduced in CTA order by
+// stem_wgrad_reduce_kernel.  Cout <= 32.
+__global__ void stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
+                                  int N, int H, int W, int Cout, int64_t pix_per_cta) {
     // blockDim = (32 channels, 8 pixel lanes)
     __shared__ float sh[8][10][33];
     const int co = threadIdx.x;
@@ -338,10 +341,19 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ x, const float* __re
             float t = 0.f;
 #pragma unroll
             for (int l = 0; l < 8; ++l) t += sh[l][i][threadIdx.x];
-            if (i < 9) atomicAdd(dw + co * 9 + i, t);
-            else atomicAdd(db + co, t);
+            part[((size_t)blockIdx.x * 10 + i) * 32 + co] = t;
         }
     }
+}
+// dw[co,0,r,s] += sum_cta part[cta][r*3+s][co];  db[co] += sum_cta part[cta][9][co]
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dw,
+                                         float* __restrict__ db, int Cout) {
+    const int co = threadIdx.x, i = blockIdx.x;   // 32 threads x 10 CTAs
+    if (co >= Cout) return;
+    float t = 0.f;
+    for (int p = 0; p < nparts; ++p) t += part[((size_t)p * 10 + i) * 32 + co];
+    if (i < 9) dw[co * 9 + i] += t;
+    else db[co] += t;
 }
 
 static inline ConvGeom make_geom(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
@@ -386,7 +398,7 @@ HA2G_API int ha2g_conv2d_dgrad(const float* dy, const float* wb, float* dx, int 
     HA2G_RETURN_LAST();
 }
 
-// dwf[KH*KW*Cin, Cout] += x^T_gathered * dy     (dwf must be initialised; split over pixels with atomics)
+// dwf[KH*KW*Cin, Cout] += x^T_gathered * dy     (dwf must be initialised; split over pixels; partial planes reduced in order)
 HA2G_API int ha2g_conv2d_wgrad(const float* x, const float* dy, float* dwf, int N, int H, int W, int Cin, int Cout,
                                int KH, int KW, int stride, int pad, cudaStream_t stream) {
     if (Cin % 16 != 0 || Cout % 4 != 0) return (int)cudaErrorInvalidValue;
@@ -401,9 +413,11 @@ HA2G_API int ha2g_conv2d_wgrad(const float* x, const float* dy, float* dwf, int 
     if (per < 256) per = 256;
     splits = (int)((P + per - 1) / per);
     dim3 grid(ha2g_div_up(Cout, bn), ha2g_div_up(Kd, CBM), splits);
-    if (bn == 64) conv2d_wgrad_kernel<64><<<grid, CNT, 0, stream>>>(x, dy, dwf, g, per);
-    else conv2d_wgrad_kernel<32><<<grid, CNT, 0, stream>>>(x, dy, dwf, g, per);
-    HA2G_RETURN_LAST();
+    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)splits * Kd * Cout * sizeof(float)));
+    if (part == nullptr) return (int)cudaErrorMemoryAllocation;
+    if (bn == 64) conv2d_wgrad_kernel<64><<<grid, CNT, 0, stream>>>(x, dy, part, g, per);
+    else conv2d_wgrad_kernel<32><<<grid, CNT, 0, stream>>>(x, dy, part, g, per);
+    return ha2g_splitk_reduce(part, splits, Kd, Cout, dwf, Cout, nullptr, 1, stream);
 }
 
 // OIHW checkpoint layout <-> GEMM layouts.  mode 0: w->wf, 1: w->wb, 2: dwf->dw
@@ -430,6 +444,9 @@ HA2G_API int ha2g_stem_conv_wgrad(const float* x, const float* dy, float* dw, fl
     int64_t per = (P + ctas - 1) / ctas;
     if (per < 64) per = 64;
     ctas = (int)((P + per - 1) / per);
-    stem_wgrad_kernel<<<ctas, dim3(32, 8), 0, stream>>>(x, dy, dw, db, N, H, W, Cout, per);
+    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)ctas * 10 * 32 * sizeof(float)));
+    if (part == nullptr) return (int)cudaErrorMemoryAllocation;
+    stem_wgrad_kernel<<<ctas, dim3(32, 8), 0, stream>>>(x, dy, part, N, H, W, Cout, per);
+    stem_wgrad_reduce_kernel<<<10, 32, 0, stream>>>(part, ctas, dw, db, Cout);
     HA2G_RETURN_LAST();
 }

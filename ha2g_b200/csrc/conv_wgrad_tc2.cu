@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(WNT, 1) conv_wgrad_tc2_kernel(const uint4* __r
         }
         __syncwarp();
     } else {
-        // ===== epilogue warps 2..5: lane = output channel, columns = (tap, input channel); fp32 atomics into dwf =====
+        // ===== epilogue warps 2..5: lane = output channel, columns = (tap, input channel); plain stores into this pixel split's partial plane =====
         const int q = warp & 3;
         const int co = co0 + q * 32 + lane;
         if (b1 > b0) {
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(WNT, 1) conv_wgrad_tc2_kernel(const uint4* __r
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int ci = ci0 + c0 + i;
-                            atomicAdd(dwf + ((size_t)tap * g.Cin + ci) * g.Cout + co, __uint_as_float(r[i]));
+                            dwf[(((size_t)blockIdx.x * g.KH * g.KW + tap) * g.Cin + ci) * g.Cout + co] = __uint_as_float(r[i]);
                         }
                     }
                 }
@@ -289,8 +289,14 @@ HA2G_API int ha2g_conv_wgrad_tc2(const float* x, const float* dy, float* dwf, in
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid(split, m_tiles, g.n_groups * n_tiles);
+    // every pixel split writes its own [KH*KW*Cin, Cout] plane; the planes are added onto dwf in split order (deterministic)
+    const int rows = KH * KW * Cin;
+    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)split * rows * Cout * sizeof(float)));
+    if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     conv_wgrad_tc2_kernel<<<grid, WNT, smem, stream>>>(reinterpret_cast<const uint4*>(xh), reinterpret_cast<const uint4*>(xl),
                                                        reinterpret_cast<const uint4*>(yh), reinterpret_cast<const uint4*>(yl),
-                                                       dwf, g, tmem_cols);
-    HA2G_RETURN_LAST();
+                                                       part, g, tmem_cols);
+    cudaError_t le = cudaPeekAtLastError();
+    if (le != cudaSuccess) return (int)le;
+    return ha2g_splitk_reduce(part, split, rows, Cout, dwf, Cout, nullptr, 1, stream);
 }

@@ -5,9 +5,11 @@
 
 namespace {
 
-__global__ void col_sum_kernel(const float* __restrict__ x, int rows, int cols, int ld, float* __restrict__ out,
-                               int rows_per_cta) {
-    // blockDim = (32, 8): 32 columns x 8 row lanes
+__global__ void col_sum_kernel(const float* __restrict__ x, int rows, int cols, int ld, float* __restrict__ dst,
+                               int rows_per_cta, int add) {
+    // blockDim = (32, 8): 32 columns x 8 row lanes.  CTA (bx, by) owns rows [by*rows_per_cta, ...) of 32 columns and writes
+    // ONE value per column: dst[by*cols + c] (add == 0: partial, reduced in order by col_sum_reduce_kernel) or, when the
+    // grid has a single row chunk, dst[c] += t.  No atomics: the result does not depend on CTA scheduling.
     __shared__ float sh[8][33];
     int c = blockIdx.x * 32 + threadIdx.x;
     int r0 = blockIdx.y * rows_per_cta;
@@ -21,8 +23,17 @@ __global__ void col_sum_kernel(const float* __restrict__ x, int rows, int cols, 
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
-        atomicAdd(out + c, t);
+        if (add) dst[c] += t;
+        else dst[(size_t)blockIdx.y * cols + c] = t;
     }
+}
+// out[c] += part[0][c] + part[1][c] + ... in index order
+__global__ void col_sum_reduce_kernel(const float* __restrict__ part, int ny, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float t = 0.f;
+    for (int y = 0; y < ny; ++y) t += part[(size_t)y * cols + c];
+    out[c] += t;
 }
 
 __global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int act) {
@@ -62,13 +73,68 @@ __global__ void embedding_fwd_kernel(const float* __restrict__ table, const int6
         out[i] = table[idx[r] * dim + c];
     }
 }
-__global__ void embedding_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ idx,
-                                     float* __restrict__ dtable, int64_t n_idx, int dim) {
-    const int64_t n = n_idx * dim;
+// Deterministic scatter-add of nn.Embedding's dense gradient.  Rows that share an index are summed by ONE CTA in
+// ascending row order (fixed 8-way interleave, combined in lane order), so the result is independent of scheduling.
+//   pass 1: head[r] = 1 iff no earlier row has the same index
+//   pass 2: CTA (r, column chunk) of a head row compacts the member rows {r'' >= r : idx[r''] == idx[r]} in order into
+//           shared memory and accumulates dout over them
+__global__ void embedding_heads_kernel(const int64_t* __restrict__ idx, int n, unsigned char* __restrict__ head) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t me = idx[r];
+    int dup = 0;
+#pragma unroll 8
+    for (int k = 0; k < r; ++k) dup |= (idx[k] == me) ? 1 : 0;   // no early exit: independent (warp-broadcast) loads
+    head[r] = dup ? 0 : 1;
+}
+__global__ void __launch_bounds__(256) embedding_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ idx,
+                                                            const unsigned char* __restrict__ head,
+                                                            float* __restrict__ dtable, int n, int dim) {
+    extern __shared__ int members[];          // [n] worst case
+    __shared__ int warp_cnt[8];
+    __shared__ float part[8][32];
+    const int r = blockIdx.x;
+    if (!head[r]) return;
+    const int64_t me = idx[r];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int count = 0;
+    for (int base = r; base < n; base += 256) {
+        const int k = base + tid;
+        const bool hit = k < n && idx[k] == me;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_cnt[w] = __popc(bal);
+        __syncthreads();
+        int off = count;
+        for (int i = 0; i < w; ++i) off += warp_cnt[i];
+        if (hit) members[off + __popc(bal & ((1u << lane) - 1u))] = k;
+        for (int i = 0; i < 8; ++i) count += warp_cnt[i];
+        __syncthreads();
+    }
+    const int c = blockIdx.y * 32 + lane;
+    float acc = 0.f;
+    if (c < dim)
+        for (int k = w; k < count; k += 8) acc += dout[(size_t)members[k] * dim + c];
+    part[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && c < dim) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][lane];
+        dtable[me * dim + c] += t;
+    }
+}
+
+// dst[g*dst_ld + dst_off + c] += sum over the `group` consecutive source rows of group g (in order): the z gradient of
+// concat_seq, where z was broadcast over T
+__global__ void sum_row_groups_kernel(const float* __restrict__ src, int src_ld, int src_off, float* __restrict__ dst,
+                                      int dst_ld, int dst_off, int64_t groups, int group, int ncols) {
+    const int64_t n = groups * ncols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / dim;
-        int c = (int)(i % dim);
-        atomicAdd(dtable + idx[r] * dim + c, dout[i]);
+        const int64_t g = i / ncols;
+        const int c = (int)(i % ncols);
+        float t = 0.f;
+        for (int k = 0; k < group; ++k) t += src[(g * group + k) * src_ld + src_off + c];
+        dst[g * dst_ld + dst_off + c] += t;
     }
 }
 
@@ -83,8 +149,7 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int src_ld, int 
         float v = src[(r / src_div) * src_ld + src_off + c];
         float* d = dst + (r / dst_div) * dst_ld + dst_off + c;
         if (mode == 0) *d = v;
-        else if (mode == 1) *d += v;
-        else atomicAdd(d, v);
+        else *d += v;
     }
 }
 
@@ -254,15 +319,24 @@ __global__ void pre_seq_bwd_kernel(const float* __restrict__ dpre, int w,
 #define EW_LAUNCH(kern, n, ...) \
     do { if ((n) > 0) kern<<<ha2g_ew_grid((n)), 256, 0, stream>>>(__VA_ARGS__); HA2G_RETURN_LAST(); } while (0)
 
-// out[c] += sum_r x[r*ld + c]   (out must be initialised by the caller; atomics across row chunks)
+// out[c] += sum_r x[r*ld + c]   (out must be initialised by the caller).  Deterministic: row chunks write partial sums
+// into the scratch arena and a second kernel adds them in chunk order.
 HA2G_API int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return 0;
     int gx = ha2g_div_up(cols, 32);
     int want_y = ha2g_div_up(148 * 4, gx);
     int rows_per = ha2g_div_up(rows, want_y);
     if (rows_per < 64) rows_per = 64;
-    dim3 grid(gx, ha2g_div_up(rows, rows_per));
-    col_sum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, cols, ld, out, rows_per);
+    const int gy = ha2g_div_up(rows, rows_per);
+    dim3 grid(gx, gy);
+    if (gy == 1) {
+        col_sum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, cols, ld, out, rows_per, 1);
+        HA2G_RETURN_LAST();
+    }
+    float* part = reinterpret_cast<float*>(ha2g_ws((size_t)gy * cols * sizeof(float)));
+    if (part == nullptr) return (int)cudaErrorMemoryAllocation;
+    col_sum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, cols, ld, part, rows_per, 0);
+    col_sum_reduce_kernel<<<ha2g_div_up(cols, 128), 128, 0, stream>>>(part, gy, cols, out);
     HA2G_RETURN_LAST();
 }
 HA2G_API int ha2g_act_fwd(const float* x, float* y, int64_t n, int act, cudaStream_t stream) {
@@ -286,14 +360,31 @@ HA2G_API int ha2g_embedding_fwd(const float* table, const int64_t* idx, float* o
                                 cudaStream_t stream) {
     EW_LAUNCH(embedding_fwd_kernel, n_idx * dim, table, idx, out, n_idx, dim);
 }
-// dtable[idx[r],:] += dout[r,:]   (dense gradient like nn.Embedding(sparse=False))
+// dtable[idx[r],:] += dout[r,:]   (dense gradient like nn.Embedding(sparse=False)); deterministic, see the kernels
 HA2G_API int ha2g_embedding_bwd(const float* dout, const int64_t* idx, float* dtable, int64_t n_idx, int dim,
                                 cudaStream_t stream) {
-    EW_LAUNCH(embedding_bwd_kernel, n_idx * dim, dout, idx, dtable, n_idx, dim);
+    if (n_idx <= 0 || dim <= 0) return 0;
+    const int n = (int)n_idx;
+    if ((size_t)n * sizeof(int) > 200 * 1024) return (int)cudaErrorInvalidValue;
+    unsigned char* head = ha2g_ws((size_t)n);
+    if (head == nullptr) return (int)cudaErrorMemoryAllocation;
+    embedding_heads_kernel<<<ha2g_div_up(n, 128), 128, 0, stream>>>(idx, n, head);
+    const size_t smem = (size_t)n * sizeof(int);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(embedding_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    embedding_bwd_kernel<<<dim3(n, ha2g_div_up(dim, 32)), 256, smem, stream>>>(dout, idx, head, dtable, n, dim);
+    HA2G_RETURN_LAST();
 }
-// mode 0: assign, 1: +=, 2: atomicAdd
+// mode 0: assign, 1: +=, 2: dst row g = r / dst_div accumulates its dst_div consecutive source rows in order (src_div == 1)
 HA2G_API int ha2g_copy_cols(const float* src, int src_ld, int src_off, int src_div, float* dst, int dst_ld, int dst_off,
                             int dst_div, int64_t rows, int ncols, int mode, cudaStream_t stream) {
+    if (mode == 2) {
+        if (src_div != 1 || dst_div < 1 || rows % dst_div != 0) return (int)cudaErrorInvalidValue;
+        const int64_t groups = rows / dst_div;
+        EW_LAUNCH(sum_row_groups_kernel, groups * ncols, src, src_ld, src_off, dst, dst_ld, dst_off, groups, dst_div, ncols);
+    }
     EW_LAUNCH(copy_cols_kernel, rows * ncols, src, src_ld, src_off, src_div, dst, dst_ld, dst_off, dst_div, rows, ncols,
               mode);
 }

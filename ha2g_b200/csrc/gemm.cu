@@ -4,7 +4,7 @@
 // (hierarchy_net.py:44,89-93,117-119,218-219; ResNetSE34V2.py:36,40,44,60-61), the GRU input
 // projections and weight gradients (K9/K11 in SURVEY.md), TCN k=2 convs as [x(t-d) | x(t)] GEMMs.
 // 128x64x16 tiles, 256 threads, 8x4 register micro-tile, guarded loads (any M,N,K, any stride),
-// optional split-K (atomicAdd) for the skinny weight-gradient shapes.
+// optional split-K (per-slice partial planes + an ordered reduction: deterministic) for the skinny weight-gradient shapes.
 #include "common.cuh"
 
 namespace {
@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(const float* __restrict__ 
                                                       float* __restrict__ C, const float* __restrict__ bias,
                                                       int M, int N, int K, int lda, int ldb, int ldc,
                                                       int act, int accumulate, int k_per_split,
-                                                      int kseg_len, int kseg_stride) {
+                                                      int kseg_len, int kseg_stride, float* __restrict__ part) {
     __shared__ __align__(16) float As[2][BK][BM + 4];
     __shared__ __align__(16) float Bs[2][BK][BN + 4];
     const int tid = threadIdx.x;
@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(const float* __restrict__ 
         buf ^= 1;
     }
 
+    // split-K: every K slice stores its tile into its own plane of `part`; ha2g_splitk_reduce adds the planes in order
     const bool split = gridDim.z > 1;
+    float* pz = split ? part + (size_t)blockIdx.z * M * N : nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         int gm = m0 + ty * 8 + i;
@@ -129,8 +131,7 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(const float* __restrict__ 
             float v = acc[i][j];
             float* dst = C + (size_t)gm * ldc + gn;
             if (split) {
-                if (bias != nullptr && blockIdx.z == 0) v += bias[gn];
-                atomicAdd(dst, v);
+                pz[(size_t)gm * N + gn] = v;
             } else {
                 if (bias != nullptr) v += bias[gn];
                 v = ha2g_act(v, act);
@@ -141,7 +142,28 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(const float* __restrict__ 
     }
 }
 
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int nz, int M, int N, float* __restrict__ C, int ldc,
+                                     const float* __restrict__ bias, int accumulate) {
+    const int64_t n = (int64_t)M * N;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e / N), c = (int)(e % N);
+        float t = 0.f;
+        for (int z = 0; z < nz; ++z) t += part[(size_t)z * n + e];
+        if (bias != nullptr) t += bias[c];
+        float* dst = C + (size_t)m * ldc + c;
+        *dst = accumulate ? *dst + t : t;
+    }
+}
+
 }  // namespace
+
+int ha2g_splitk_reduce(const float* part, int nz, int M, int N, float* C, int ldc, const float* bias, int accumulate,
+                       cudaStream_t stream) {
+    const int64_t n = (int64_t)M * N;
+    if (n <= 0) return 0;
+    splitk_reduce_kernel<<<ha2g_ew_grid(n, 256, 2), 256, 0, stream>>>(part, nz, M, N, C, ldc, bias, accumulate);
+    HA2G_RETURN_LAST();
+}
 
 // C-ABI.  Row-major everywhere.  transA: A is stored [K][M] (lda >= M) else [M][K] (lda >= K);
 // transB: B is stored [N][K] (ldb >= K) else [K][N] (ldb >= N).  split_k > 1 requires act == 0 and a
@@ -160,12 +182,18 @@ HA2G_API int ha2g_gemm_f32_kseg(const float* A, const float* B, float* C, const 
     if (k_per < BK) k_per = BK;
     int nz = K > 0 ? (K + k_per - 1) / k_per : 1;
     dim3 grid(ha2g_div_up(N, BN), ha2g_div_up(M, BM), nz);
+    float* part = nullptr;
+    if (nz > 1) {
+        part = reinterpret_cast<float*>(ha2g_ws_top((size_t)nz * M * N * sizeof(float)));
+        if (part == nullptr) return (int)cudaErrorMemoryAllocation;
+    }
 #define LAUNCH(TA_, TB_) \
     gemm_f32_kernel<TA_, TB_><<<grid, NT, 0, stream>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, act, accumulate, k_per, \
-                                                       kseg_len, kseg_stride)
+                                                       kseg_len, kseg_stride, part)
     if (transA) { if (transB) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (transB) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
+    if (nz > 1) return ha2g_splitk_reduce(part, nz, M, N, C, ldc, bias, accumulate, stream);
     HA2G_RETURN_LAST();
 }
 

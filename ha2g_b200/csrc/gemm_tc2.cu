@@ -7,7 +7,7 @@
 //   gemm  : C[M,N] (+)= act(A B^T + bias) with A = (A_hi, A_lo) [M x K], B = (B_hi, B_lo) [N x K] packed as above.
 //           Warp-specialised: warp 0 = bulk-copy producer (one thread, mbarrier expect_tx), warp 1 = MMA issuer (one
 //           thread; per 16-wide K step hi*hi + hi*lo + lo*hi into one TMEM accumulator, or hi*hi only in bf16 mode),
-//           warps 2-5 = epilogue (tcgen05.ld 32 lanes x 32 columns, bias/activation, fp32 store or atomic split-K).
+//           warps 2-5 = epilogue (tcgen05.ld 32 lanes x 32 columns, bias/activation, fp32 store; split-K slices store partial planes that are reduced in order).
 //           3-stage shared-memory ring (96 KB at BN = 128 -> two CTAs per SM so one CTA's epilogue hides under the
 //           other's main loop).  No thread touches operand data: the SM only issues copies and MMAs.
 // This replaces the register-staged kernel of gemm_tc.cu (producer-bound at ~50 TFLOP/s: every CTA re-converted its
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
                                                           const uint4* __restrict__ b_lo, int rows_pb,
                                                           float* __restrict__ C, const float* __restrict__ bias, int M,
                                                           int N, int chunks_p, int ldc, int act, int accumulate,
-                                                          int stages_per_split) {
+                                                          int stages_per_split, float* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char smem[];
     using S = PSmem<BN>;
     constexpr int PST = S::NSTAGE;
@@ -217,7 +217,12 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
             mb_wait(bar_done, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const bool split = gridDim.z > 1;
+        // split-K: this K slice stores its plain tile into plane blockIdx.z of `part` (ha2g_splitk_reduce then adds the
+        // planes in order, with the bias): no atomics, the result does not depend on CTA scheduling
+        if (gridDim.z > 1) {
+            C = part + (size_t)blockIdx.z * M * N;
+            ldc = N; bias = nullptr; act = 0; accumulate = 0;
+        }
         // The accumulator arrives one ROW per thread (TMEM lane = row).  Writing it out that way makes every store
         // instruction touch 32 different lines; instead each warp transposes its 32 x 32 block through shared memory (the
         // operand ring is idle once bar_done has fired) and writes 128 contiguous bytes per row: 8x fewer L1 wavefronts.
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
             for (int i = 0; i < 32; i += 4)
                 *reinterpret_cast<uint4*>(stg + (size_t)lane * SP + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
             __syncwarp();
-            const bool vec = !split && ((ldc & 3) == 0) && (n0 + c0 + 32 <= N) && ((((uintptr_t)C) & 15) == 0) &&
+            const bool vec = ((ldc & 3) == 0) && (n0 + c0 + 32 <= N) && ((((uintptr_t)C) & 15) == 0) &&
                              (bias == nullptr || (((uintptr_t)bias) & 15) == 0);
             if (vec) {
                 const int col = n0 + c0 + c4 * 4;
@@ -269,19 +274,16 @@ __global__ void __launch_bounds__(PNT) gemm_packed_kernel(const uint4* __restric
             } else {
                 const int col = n0 + c0 + lane;
                 if (col < N) {
-                    const float bvs = (bias != nullptr && (!split || blockIdx.z == 0)) ? bias[col] : 0.f;
+                    const float bvs = bias != nullptr ? bias[col] : 0.f;
 #pragma unroll 4
                     for (int rl = 0; rl < 32; ++rl) {
                         const int grow = m0 + q * 32 + rl;
                         if (grow < M) {
                             float v = stg[(size_t)rl * SP + lane] + bvs;
                             float* dst = C + (size_t)grow * ldc + col;
-                            if (split) atomicAdd(dst, v);
-                            else {
-                                v = ha2g_act(v, act);
-                                if (accumulate) v += *dst;
-                                *dst = v;
-                            }
+                            v = ha2g_act(v, act);
+                            if (accumulate) v += *dst;
+                            *dst = v;
                         }
                     }
                 }
@@ -303,17 +305,22 @@ static int launch_packed(const void* a_hi, const void* a_lo, int rows_pa, const 
     const int total_stages = chunks_p / (PBK / 8);
     if (split_k < 1) split_k = 1;
     if (split_k > total_stages) split_k = total_stages > 0 ? total_stages : 1;
-    if (split_k > 1) accumulate = 1;
     const int per = (total_stages + split_k - 1) / split_k;
     const int nz = total_stages > 0 ? (total_stages + per - 1) / per : 1;
     dim3 grid(ha2g_div_up(N, BN), ha2g_div_up(M, PBM), nz);
     const int smem = PSmem<BN>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(gemm_packed_kernel<BN, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
+    float* part = nullptr;
+    if (nz > 1) {
+        part = reinterpret_cast<float*>(ha2g_ws_top((size_t)nz * M * N * sizeof(float)));
+        if (part == nullptr) return (int)cudaErrorMemoryAllocation;
+    }
     gemm_packed_kernel<BN, TERMS><<<grid, PNT, smem, stream>>>(
         reinterpret_cast<const uint4*>(a_hi), reinterpret_cast<const uint4*>(a_lo), rows_pa,
         reinterpret_cast<const uint4*>(b_hi), reinterpret_cast<const uint4*>(b_lo), rows_pb, C, bias, M, N, chunks_p, ldc, act,
-        accumulate, per > 0 ? per : 1);
+        accumulate, per > 0 ? per : 1, part);
+    if (nz > 1) return ha2g_splitk_reduce(part, nz, M, N, C, ldc, bias, accumulate, stream);
     HA2G_RETURN_LAST();
 }
 
@@ -370,11 +377,19 @@ HA2G_API int ha2g_gemm_packed(const void* a_hi, const void* a_lo, int rows_pa, c
     return launch_packed<64, 1>(a_hi, a_lo, rows_pa, b_hi, b_lo, rows_pb, C, bias, M, N, chunks_p, ldc, act, accumulate, split_k, stream);
 }
 
-// Scratch arena for the packing passes: the host registers ONE device buffer (torch-allocated) per process; calls on the
-// same stream reuse it safely (stream order).  Without a (large enough) arena the call falls back to a stream-ordered
-// cudaMallocAsync/cudaFreeAsync pair (~60 us of allocator latency per call, measured).
+// Scratch arena for the packing passes and the deterministic reductions: the host registers ONE device buffer
+// (torch-allocated) per process; calls on the same stream reuse it safely (stream order).  The launchers allocate nothing:
+// without a large enough arena they return cudaErrorMemoryAllocation.  Bottom 3/4: packed operands / reduction partials of
+// one launcher call; top 1/4: split-K partial planes.
 static unsigned char* g_ws = nullptr;
 static size_t g_ws_bytes = 0;
+static inline size_t ws_top_bytes() { return (g_ws_bytes / 4) & ~(size_t)255; }
+unsigned char* ha2g_ws(size_t need_bytes) {
+    return (g_ws != nullptr && need_bytes <= g_ws_bytes - ws_top_bytes()) ? g_ws : nullptr;
+}
+unsigned char* ha2g_ws_top(size_t need_bytes) {
+    return (g_ws != nullptr && need_bytes <= ws_top_bytes()) ? g_ws + (g_ws_bytes - ws_top_bytes()) : nullptr;
+}
 HA2G_API int ha2g_set_workspace(void* ptr, int64_t bytes) {
     g_ws = reinterpret_cast<unsigned char*>(ptr);
     g_ws_bytes = ptr != nullptr ? (size_t)bytes : 0;
@@ -392,12 +407,8 @@ HA2G_API int ha2g_gemm_tc2(const float* A, const float* B, float* C, const float
     ha2g_pack_dims(N, K, &rpb, &cp2);
     const size_t a_bytes = (size_t)rpa * cp * 16, b_bytes = (size_t)rpb * cp * 16;
     const size_t need = 2 * (a_bytes + b_bytes);
-    unsigned char* ws = g_ws;
-    const bool own = (ws == nullptr || need > g_ws_bytes);
-    if (own) {
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), need, stream);
-        if (e != cudaSuccess) return (int)e;
-    }
+    unsigned char* ws = ha2g_ws(need);
+    if (ws == nullptr) return (int)cudaErrorMemoryAllocation;   // the arena (ha2g_set_workspace) is missing or too small
     unsigned char *ah = ws, *al = ws + a_bytes, *bh = ws + 2 * a_bytes, *bl = ws + 2 * a_bytes + b_bytes;
     // skinny outputs with a long reduction (e.g. the 4032->32 head projections): too few output tiles to fill 148 SMs,
     // so split K automatically (needs a zero-initialised C and no activation)
@@ -409,21 +420,11 @@ HA2G_API int ha2g_gemm_tc2(const float* A, const float* B, float* C, const float
             int s = 148 / tiles;
             if (s > 8) s = 8;
             if (s > stages / 4) s = stages / 4;
-            if (s > 1) {
-                if (!accumulate) {
-                    cudaError_t em = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
-                    if (em != cudaSuccess) return (int)em;
-                }
-                split_k = s;
-            }
+            if (s > 1) split_k = s;   // the ordered reduction overwrites C when accumulate == 0
         }
     }
     int rc = ha2g_pack_bf16x2(A, lda, M, K, transA ? 0 : 1, kseg_len, kseg_stride, ah, al, stream);
     if (rc == 0) rc = ha2g_pack_bf16x2(B, ldb, N, K, transB ? 1 : 0, kseg_len, kseg_stride, bh, bl, stream);
     if (rc == 0) rc = ha2g_gemm_packed(ah, al, rpa, bh, bl, rpb, C, bias, M, N, cp, ldc, act, accumulate, split_k, terms, stream);
-    if (own) {
-        cudaError_t e2 = cudaFreeAsync(ws, stream);
-        if (rc == 0) rc = (int)e2;
-    }
     return rc;
 }

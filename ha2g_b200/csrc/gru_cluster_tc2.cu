@@ -45,7 +45,6 @@ struct Tc2Params {
     float* gates;          // [M,T,2,4H] or nullptr
     int M, T, H, HSP, n_chunks;
     long long* dbg;        // optional [T+1][8] clock64 samples of cluster 0 / rank 0 (phase timing), nullptr otherwise
-    int flags;             // timing experiments only (HA2G_GRU_DBGFLAGS): 1 = skip the y/gates copy-out, 2 = skip staging too
 };
 
 __device__ __forceinline__ uint32_t su32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,7 +171,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
     float* __restrict__ g_y = p.y;
     float* __restrict__ g_gates = p.gates;
     long long* g_dbg = p.dbg;
-    const int g_flags = g_flags;
     const uint32_t tx_bytes = (uint32_t)(CL * L.slice_bytes);
 
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
@@ -432,7 +430,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                 {
                     const int OR = L.orow;
                     const int narr = g_gates != nullptr ? 5 : 1;
-                    if (has_item && !(g_flags & 2)) {
+                    if (has_item) {
                         float* o = outst + (size_t)bb * OR + cc * 8;
                         reinterpret_cast<float4*>(o)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
                         reinterpret_cast<float4*>(o)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
@@ -452,7 +450,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                     // copy-out: thread -> up to two fixed (batch row, float4) positions of every line group
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        if (k < co_n && !(g_flags & 1)) {
+                        if (k < co_n) {
                             const int rb = co_rb[k], f4 = co_f4[k];
                             const int bg = m0 + rb, jg = j0 + f4 * 4;
                             if (bg < M && jg < H) {               // H % 4 == 0: a float4 is entirely valid or entirely padding
@@ -513,7 +511,6 @@ HA2G_API int ha2g_gru_seq_fwd_tc2_dbg(const float* gi, const float* w_hh_f, cons
                                       cudaStream_t stream) {
     Tc2Params p{};
     p.dbg = dbg;
-    { const char* e = dbg != nullptr ? getenv("HA2G_GRU_DBGFLAGS") : nullptr; p.flags = e != nullptr ? atoi(e) : 0; }
     p.gi = gi; p.w_hh[0] = w_hh_f; p.w_hh[1] = w_hh_r; p.b_hh[0] = b_hh_f; p.b_hh[1] = b_hh_r;
     p.y = y; p.gates = gates; p.M = M; p.T = T; p.H = H;
     p.HSP = ((H + CL - 1) / CL + 7) / 8 * 8;

@@ -12,6 +12,40 @@
 
 namespace {
 
+// Deterministic grid-wide accumulation of one value per CTA into a device scalar: every CTA stores its partial, takes an
+// integer ticket, and the LAST CTA to arrive adds the partials in a fixed pattern (lane-strided, then a shuffle tree) --
+// the result does not depend on the order in which the CTAs ran.  One scratch serves every loss kernel: they are issued
+// on one stream (or one captured chain), never concurrently.
+constexpr int RED_MAX = 4096;
+__device__ float g_red_part[RED_MAX];
+__device__ unsigned int g_red_ticket;
+__device__ __forceinline__ void grid_accumulate(float block_val /* valid in thread 0 */, float* __restrict__ loss) {
+    __shared__ int s_last;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const unsigned nblk = gridDim.x * gridDim.y;
+    const unsigned bid = blockIdx.x + blockIdx.y * gridDim.x;
+    if (nblk == 1) {
+        if (tid == 0) *loss += block_val;
+        return;
+    }
+    if (tid == 0) {
+        g_red_part[bid] = block_val;
+        __threadfence();
+        s_last = atomicAdd(&g_red_ticket, 1u) == nblk - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last && tid < 32) {
+        __threadfence();
+        float t = 0.f;
+        for (unsigned i = tid; i < nblk; i += 32) t += reinterpret_cast<volatile float*>(g_red_part)[i];
+        t = warp_sum(t);
+        if (tid == 0) {
+            *loss += t;
+            g_red_ticket = 0u;
+        }
+    }
+}
+
 // loss += beta * mean(smooth_l1((o-t)/beta));  grad[i] = clamp((o-t)/beta, -1, 1) / n
 __global__ void huber_kernel(const float* __restrict__ o, const float* __restrict__ t, float* __restrict__ grad, int64_t n,
                              float beta, float* __restrict__ loss) {
@@ -25,7 +59,7 @@ __global__ void huber_kernel(const float* __restrict__ o, const float* __restric
         if (grad != nullptr) grad[i] = fminf(fmaxf(x, -1.f), 1.f) * invn;
     }
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) atomicAdd(loss, acc * beta * invn);
+    grid_accumulate(acc * beta * invn, loss);
 }
 
 // mode 0: loss += -mean(log(x + 1e-8)),     grad = -1/(n (x+1e-8))
@@ -48,7 +82,7 @@ __global__ void log_loss_kernel(const float* __restrict__ x, float* __restrict__
         }
     }
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) atomicAdd(loss, acc * invn);
+    grid_accumulate(acc * invn, loss);
 }
 
 // kld = -0.5 * mean(1 + lv - mu^2 - exp(lv));  dmu = mu/n;  dlv = -0.5 (1 - exp(lv))/n
@@ -64,7 +98,7 @@ __global__ void kld_kernel(const float* __restrict__ mu, const float* __restrict
         dlv[i] = -0.5f * (1.f - e) * invn;
     }
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) atomicAdd(loss, -0.5f * acc * invn);
+    grid_accumulate(-0.5f * acc * invn, loss);
 }
 
 // one CTA per sample b:  pose_l1 = sum_{t,d} beta*smooth_l1((o-r)/beta);  z_l1 = mean_j |z - zr|
@@ -88,12 +122,12 @@ __global__ void div_reg_kernel(const float* __restrict__ o, const float* __restr
     const float den = zl1 + 1.0e-5f;
     const float val = -pose / den;
     const bool live = val >= -1000.f;
-    if (threadIdx.x == 0) atomicAdd(loss, fmaxf(val, -1000.f) / (float)B);
     const float coef = live ? -1.f / (den * (float)B) : 0.f;
     for (int e = threadIdx.x; e < TD; e += blockDim.x) {
         float x = o[(size_t)b * TD + e] * invb - r[(size_t)b * TD + e] * invb;
         grad[(size_t)b * TD + e] = coef * fminf(fmaxf(x, -1.f), 1.f);
     }
+    grid_accumulate(fmaxf(val, -1000.f) / (float)B, loss);
 }
 
 __global__ void scale_by_scalar_kernel(const float* __restrict__ x, const float* __restrict__ s, float alpha,
@@ -205,11 +239,10 @@ __global__ void physical_kernel(const float* __restrict__ out, float* __restrict
         for (int e = lane; e < D; e += 32) grad[row * D + e] = dun[w][e];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
+    float t = 0.f;
+    if (threadIdx.x == 0)
         for (int i = 0; i < WPB; ++i) t += wl[i];
-        atomicAdd(loss, t * inv_rows);
-    }
+    grid_accumulate(t * inv_rows, loss);
 }
 
 // ---- contrastive --------------------------------------------------------------------------------------
@@ -227,13 +260,16 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ x, float* __restric
     xn[row * CC + lane] = v / n;
     if (lane == 0) nrm[row] = n;
 }
-// dx = (dn - (dn . n) n) / norm
-__global__ void l2norm_rows_bwd_kernel(const float* __restrict__ dn, const float* __restrict__ xn,
+// dx = (dn - (dn . n) n) / norm, with dn = the sum of `planes` partial planes [planes][N][32] added in index order (the
+// column splits of contrastive_pair_kernel<1> each write their own plane: no atomics)
+__global__ void l2norm_rows_bwd_kernel(const float* __restrict__ dn, int planes, const float* __restrict__ xn,
                                        const float* __restrict__ nrm, float* __restrict__ dx, int64_t N) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (row >= N) return;
-    float g = dn[row * CC + lane], n = xn[row * CC + lane];
+    float g = 0.f;
+    for (int p = 0; p < planes; ++p) g += dn[((size_t)p * N + row) * CC + lane];
+    const float n = xn[row * CC + lane];
     float dot = warp_sum(g * n);
     dx[row * CC + lane] = (g - dot * n) / nrm[row];
 }
@@ -317,7 +353,7 @@ __global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __res
         part[((size_t)i * gridDim.y + blockIdx.y) * 2 + 1] = s;
     } else {
 #pragma unroll
-        for (int c = 0; c < CC; ++c) atomicAdd(dgrad + (size_t)i * CC + c, acc[c]);
+        for (int c = 0; c < CC; ++c) dgrad[((size_t)blockIdx.y * N + i) * CC + c] = acc[c];
     }
 }
 
@@ -336,7 +372,7 @@ __global__ void contrastive_finalize_kernel(const float* __restrict__ part, cons
         acc += l - diag[i];
     }
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) atomicAdd(loss, acc / (float)N);
+    grid_accumulate(acc / (float)N, loss);
 }
 
 }  // namespace
@@ -360,6 +396,7 @@ HA2G_API int ha2g_kld(const float* mu, const float* logvar, float* dmu, float* d
 // o, r: [B,TD];  z, zr: [B,Z];  grad [B,TD] = d loss / d o (unscaled);  loss ACCUMULATED
 HA2G_API int ha2g_div_reg(const float* o, const float* r, const float* z, const float* zr, float* grad, int B, int TD,
                           int Z, float beta, float* loss, cudaStream_t stream) {
+    if (B > RED_MAX) return (int)cudaErrorInvalidValue;
     div_reg_kernel<<<B, 256, 0, stream>>>(o, r, z, zr, grad, B, TD, Z, beta, loss);
     HA2G_RETURN_LAST();
 }
@@ -387,6 +424,7 @@ HA2G_API int ha2g_physical_set_tables(int variant, const int* pairs, const float
 // out [rows, 3*nb]; loss ACCUMULATED += sum_p mean_rows((angle_p - avg_p)^2 / (2 var_p)); grad nullable, unscaled
 HA2G_API int ha2g_physical(const float* out, float* grad, int64_t rows, int variant, int nb, int npairs, float* loss,
                            cudaStream_t stream) {
+    if (ha2g_div_up(rows, 4) > RED_MAX) return (int)cudaErrorInvalidValue;
     physical_kernel<<<ha2g_div_up(rows, 4), 128, 0, stream>>>(out, grad, rows, variant, nb, npairs, loss);
     HA2G_RETURN_LAST();
 }
@@ -430,10 +468,16 @@ HA2G_API int ha2g_contrastive_bwd_rect(const float* an, const float* bn, const f
     };
     const int cols_a = splits(Na, Nb), cols_b = splits(Nb, Na);
     dim3 grid_a(ha2g_div_up(Na, CT), ha2g_div_up(Nb, cols_a)), grid_b(ha2g_div_up(Nb, CT), ha2g_div_up(Na, cols_b));
-    contrastive_pair_kernel<1><<<grid_a, CT, 0, stream>>>(an, bn, lse, nullptr, nullptr, dan, gscale, Na, variant, 1, cols_a, Nb, off);
-    contrastive_pair_kernel<1><<<grid_b, CT, 0, stream>>>(bn, an, lse, nullptr, nullptr, dbn, gscale, Nb, variant, 0, cols_b, Na, off);
-    l2norm_rows_bwd_kernel<<<ha2g_div_up(Na, 8), 256, 0, stream>>>(dan, an, na, da, Na);
-    l2norm_rows_bwd_kernel<<<ha2g_div_up(Nb, 8), 256, 0, stream>>>(dbn, bn, nb, db, Nb);
+    // per-column-split gradient planes in the scratch arena (dan / dbn of the signature are no longer needed)
+    (void)dan; (void)dbn;
+    const size_t pa = (size_t)grid_a.y * Na * CC, pb = (size_t)grid_b.y * Nb * CC;
+    float* plane_a = reinterpret_cast<float*>(ha2g_ws((pa + pb) * sizeof(float)));
+    if (plane_a == nullptr) return (int)cudaErrorMemoryAllocation;
+    float* plane_b = plane_a + pa;
+    contrastive_pair_kernel<1><<<grid_a, CT, 0, stream>>>(an, bn, lse, nullptr, nullptr, plane_a, gscale, Na, variant, 1, cols_a, Nb, off);
+    contrastive_pair_kernel<1><<<grid_b, CT, 0, stream>>>(bn, an, lse, nullptr, nullptr, plane_b, gscale, Nb, variant, 0, cols_b, Na, off);
+    l2norm_rows_bwd_kernel<<<ha2g_div_up(Na, 8), 256, 0, stream>>>(plane_a, (int)grid_a.y, an, na, da, Na);
+    l2norm_rows_bwd_kernel<<<ha2g_div_up(Nb, 8), 256, 0, stream>>>(plane_b, (int)grid_b.y, bn, nb, db, Nb);
     HA2G_RETURN_LAST();
 }
 // Streaming SoftmaxContrastiveLoss forward (replaces criterion(text_feat, feat_*) at

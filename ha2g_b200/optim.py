@@ -35,7 +35,7 @@ def fused_adam_step(optimizer: torch.optim.Optimizer):
         if not params:
             continue
         dev = params[0].device
-        rows, sizes = [], []
+        rows, sizes, keep = [], [], []
         step = None
         for p in params:
             st = optimizer.state[p]
@@ -50,6 +50,7 @@ def fused_adam_step(optimizer: torch.optim.Optimizer):
             elif s != step:
                 raise NotImplementedError("parameters of one group must share the Adam step count")
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            keep.append(g)   # a contiguous COPY must stay alive until the launch below has been enqueued
             if not p.is_contiguous():
                 raise RuntimeError("fused_adam_step needs contiguous parameters")
             rows.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()))
@@ -79,6 +80,7 @@ def fused_adam_step(optimizer: torch.optim.Optimizer):
             c["evt"] = torch.cuda.Event()
             c["evt"].record()
             c["rows"] = rows
+        c["keep"] = keep
         b1, b2 = group["betas"]
         _call("ha2g_adam_multi", _p(c["table"]), _p(c["sizes_t"]), _p(c["ct"]), _p(c["co"]), c["n"], float(group["lr"]),
               float(b1), float(b2), float(group["eps"]), step, _st())

@@ -13,6 +13,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+# Unit-level parity first, whole-step machinery last: with `-x` a failure in the CUDA-graph tests must not hide the kernel,
+# mel and inference tests behind it.
+_ORDER = ["test_boundary", "test_oracle_pinned", "test_mel", "test_kernels", "test_gpu_parity", "test_synthesize",
+          "test_evaluate", "test_fgd", "test_checkpoint", "test_data", "test_dp_gloo", "test_dp_nccl", "test_b128_parity",
+          "test_graph_step"]
+
+
+def pytest_collection_modifyitems(session, config, items):
+    def key(item):
+        mod = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+        return _ORDER.index(mod) if mod in _ORDER else len(_ORDER) - 1
+    items.sort(key=key)   # stable: keeps the order inside each module
+
+
 @pytest.fixture(scope="session")
 def golden_modules():
     import torch
