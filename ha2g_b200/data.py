@@ -91,7 +91,16 @@ def write_shard(path: str, samples: List[Tuple]) -> None:
             for i, s in enumerate(samples)]
     np.savez(path, pose=cat(pose).astype(np.float32), pose_off=off(pose), vec=cat(vec).astype(np.float32), vec_off=off(vec),
              audio=cat(audio).astype(np.float32), audio_off=off(audio), spec=cat(spec).astype(np.float16), spec_off=off(spec),
-             meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+             meta=np.frombuffer(json.dumps(meta, default=_json_default).encode(), dtype=np.uint8))
+
+
+def _json_default(o):
+    """aux_info values arrive as numpy scalars / arrays from the preprocessor's arithmetic."""
+    if isinstance(o, np.generic):
+        return o.item()
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    raise TypeError(f"Object of type {type(o).__name__} is not JSON serializable")
 
 
 class SpeechMotionShardDataset(Dataset):

@@ -75,7 +75,6 @@ def evaluate_testset(test_data_loader, generator, *rest, sigma=0.1, thres=0.03):
     gens = list(rest[:L])
     audio_encoder, _loss_fn, embed_space_evaluator, args = rest[L:]
     dev = next(gens[0].parameters()).device
-    was_training = [m.training for m in gens + [audio_encoder]]
     for m in gens + [audio_encoder]:
         m.train(False)
     if embed_space_evaluator:
@@ -83,7 +82,10 @@ def evaluate_testset(test_data_loader, generator, *rest, sigma=0.1, thres=0.03):
     losses, joint_mae, accel, bc = AverageMeter("loss"), AverageMeter("mae_on_joint"), AverageMeter("accel"), AverageMeter("bc")
     start = time.time()
     mean_dir_vec = np.array(args.mean_dir_vec).squeeze()
-    speaker_model = getattr(getattr(audio_encoder, "feat_extractor", audio_encoder), "z_obj", None)
+    enc = getattr(audio_encoder, "module", audio_encoder)   # DataParallel-wrapped encoders (train_expressive.py:431-434)
+    speaker_model = getattr(getattr(enc, "feat_extractor", enc), "z_obj", None)
+    if speaker_model is None:
+        raise NotImplementedError("the hierarchy path needs a speaker model (z_type = 'speaker')")
 
     for data in test_data_loader:
         _in_text, _text_lengths, in_text_padded, _, target_vec, in_audio, in_spec, _aux = data
@@ -91,8 +93,6 @@ def evaluate_testset(test_data_loader, generator, *rest, sigma=0.1, thres=0.03):
         in_text_padded = in_text_padded.to(dev)
         in_spec = in_spec.float().to(dev)
         target = target_vec.to(dev).float()
-        if speaker_model is None:
-            raise NotImplementedError("the hierarchy path needs a speaker model (z_type = 'speaker')")
         ids = list(speaker_model.word2index.values())
         vid_indices = torch.LongTensor([random.choice(ids) for _ in range(batch_size)]).to(dev)
 
@@ -110,8 +110,8 @@ def evaluate_testset(test_data_loader, generator, *rest, sigma=0.1, thres=0.03):
         joint_mae.update(mae, batch_size)
         accel.update(acc, batch_size)
 
-    for m, flag in zip(gens + [audio_encoder], was_training):
-        m.train(flag)
+    for m in gens + [audio_encoder]:   # the reference switches back to train mode unconditionally (train_expressive.py:601-607)
+        m.train(True)
     ret_dict = {"loss": losses.avg, "joint_mae": joint_mae.avg}
     elapsed = time.time() - start
     if embed_space_evaluator and embed_space_evaluator.get_no_of_samples() > 0:

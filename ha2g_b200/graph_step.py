@@ -37,6 +37,7 @@ MAX_GRAPHS = 4      # captured signatures kept alive (each holds one step's acti
 _state = {"enabled": os.environ.get("HA2G_CUDA_GRAPH", "1") != "0"}
 _graphs: Dict[tuple, dict] = {}
 _seen: Dict[tuple, int] = {}
+_failed: set = set()
 STATS = {"captures": 0, "replays": 0}
 
 
@@ -52,6 +53,7 @@ def reset():
     """Drop every captured graph (frees their private memory pools)."""
     _graphs.clear()
     _seen.clear()
+    _failed.clear()
 
 
 _ARG_KEYS = ("loss_warmup", "n_pre_poses", "loss_gan_weight", "loss_contrastive_pos_weight", "loss_contrastive_neg_weight",
@@ -66,7 +68,8 @@ def _signature(world):
             tuple(repr(getattr(args, k, None)) for k in _ARG_KEYS), repr(getattr(args, "mean_dir_vec", None)),
             tuple(in_text.shape), tuple(in_spec.shape), tuple(target.shape), tuple(vid.shape), str(target.device),
             tuple(id(m) for m in mods), tuple(m.training for m in mods),
-            tuple(id(o) for o in list(gopts) + [dopt, aopt, topt]), dp.world_size(), _ops.config_signature())
+            tuple(id(o) for o in list(gopts) + [dopt, aopt, topt]), dp.world_size(), _ops.config_signature(),
+            bool(rng.dropout_enabled()))
 
 
 def _eligible(world) -> bool:
@@ -86,11 +89,35 @@ def run(enqueue, world) -> Optional[tuple]:
     ent = _graphs.get(key)
     if ent is None:
         n = _seen.get(key, 0)
-        if n < WARMUP or len(_graphs) >= MAX_GRAPHS:
+        if n < WARMUP or len(_graphs) >= MAX_GRAPHS or key in _failed:
             _seen[key] = n + 1
             return None
-        ent = _capture(enqueue, world, key)
+        try:
+            ent = _capture(enqueue, world, key)
+        except Exception:
+            _failed.add(key)   # do not retry the capture on every later step; the caller runs this signature eagerly
+            raise
+    if not _still_valid(ent):
+        # parameters or Adam moments were re-allocated (optimizer.load_state_dict, module.to(...)): the addresses baked
+        # into the graph are stale -- drop it and warm up again
+        del _graphs[key]
+        _seen[key] = 1
+        return None
     return _replay(ent, world)
+
+
+def _still_valid(ent) -> bool:
+    for o in ent["opts"]:
+        for group, e in zip(o.param_groups, ent["adam"][id(o)]):
+            if e is None:
+                continue
+            rows = e["rows"]
+            for i, p in enumerate(e["params"]):
+                st = o.state.get(p)
+                if st is None or p.data_ptr() != rows[4 * i] or st["exp_avg"].data_ptr() != rows[4 * i + 2] or \
+                        st["exp_avg_sq"].data_ptr() != rows[4 * i + 3]:
+                    return False
+    return True
 
 
 def _capture(enqueue, world, key) -> dict:

@@ -28,6 +28,8 @@ def zero_grad(optimizer: torch.optim.Optimizer):
 
 @torch.no_grad()
 def fused_adam_step(optimizer: torch.optim.Optimizer):
+    """Eager step.  Runs the SAME kernels as the captured step (``ha2g_adam_multi_dev``: step counter, hyper-parameters and
+    bias corrections in device memory), so an eager step and a CUDA-graph replay of it are bit-identical."""
     for gi, group in enumerate(optimizer.param_groups):
         if group.get("amsgrad", False) or group.get("weight_decay", 0) != 0 or group.get("maximize", False):
             raise NotImplementedError("fused_adam_step covers the reference's configuration (plain Adam)")
@@ -69,6 +71,8 @@ def fused_adam_step(optimizer: torch.optim.Optimizer):
                  "co": torch.tensor(co, dtype=torch.int64, device=dev), "n": len(ct),
                  "pin": torch.empty((len(sizes) * 4,), dtype=torch.int64).pin_memory(),
                  "table": torch.empty((len(sizes) * 4,), dtype=torch.int64, device=dev),
+                 "hyper": torch.zeros((8,), dtype=torch.float64, device=dev), "hyper_host": None,
+                 "step": torch.zeros((1,), dtype=torch.int32, device=dev), "step_host": 0,
                  "keep": None}
             _cache[key] = c
         if c["rows"] != rows:
@@ -81,9 +85,15 @@ def fused_adam_step(optimizer: torch.optim.Optimizer):
             c["evt"].record()
             c["rows"] = rows
         c["keep"] = keep
-        b1, b2 = group["betas"]
-        _call("ha2g_adam_multi", _p(c["table"]), _p(c["sizes_t"]), _p(c["ct"]), _p(c["co"]), c["n"], float(group["lr"]),
-              float(b1), float(b2), float(group["eps"]), step, _st())
+        hh = _hyper_of(group)
+        if hh != c["hyper_host"]:
+            c["hyper"][:4].copy_(torch.tensor(hh, dtype=torch.float64))
+            c["hyper_host"] = hh
+        if c["step_host"] != step - 1:   # the kernel increments the device counter itself
+            c["step"].fill_(step - 1)
+        c["step_host"] = step
+        _call("ha2g_adam_multi_dev", _p(c["table"]), _p(c["sizes_t"]), _p(c["ct"]), _p(c["co"]), c["n"], _p(c["hyper"]),
+              _p(c["step"]), _st())
 
 
 # ----------------------------------------------------------------------------------------------------------------

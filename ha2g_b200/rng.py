@@ -46,6 +46,10 @@ def dropout_state(device) -> torch.Tensor:
     key = str(device)
     if key not in _dev_state:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        # data-parallel ranks usually share torch.manual_seed: fold the rank in so that every rank draws its own masks
+        # (the reference's DataParallel replicas draw independent dropout streams too)
+        from . import dp
+        seed = (seed ^ (dp.rank() * 0x9E3779B97F4A7C15)) & (2 ** 62 - 1)
         _dev_state[key] = torch.tensor([seed, 0], dtype=torch.int64, device=device)
     return _dev_state[key]
 

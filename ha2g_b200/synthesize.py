@@ -85,7 +85,10 @@ def generate_gestures_hierarchy(args, *rest, audio_sr=16000, vid=None, fade_out=
     fps = args.motion_resampling_framerate
     pose_dim = len(args.mean_dir_vec)
 
-    audio_t = torch.as_tensor(np.asarray(audio), dtype=torch.float32).to(dev)
+    if torch.is_tensor(audio):   # already a tensor (pinned host or device-resident clip): no numpy round trip
+        audio_t = audio.to(device=dev, dtype=torch.float32, non_blocking=True)
+    else:
+        audio_t = torch.as_tensor(np.asarray(audio), dtype=torch.float32).to(dev)
     spectrogram = mel.extract_melspectrogram(audio_t)  # [128, frames] on the device
     plan = window_plan(len(audio), audio_sr, n_frames, n_pre, fps, spectrogram.shape[0])
     spec_len = mel.calc_spectrogram_length_from_motion_length(n_frames, fps)

@@ -461,3 +461,69 @@ def train_step(variant: str, args, epoch: int, text: Tensor, spec: Tensor, targe
              "audio": {k: v.grad for k, v in audio.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None},
              "text": {k: v.grad for k, v in textenc.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}}
     return ret, {"gens": [det(g) for g in new_gens], "dis": det(dis), "audio": det(new_audio), "text": det(new_text)}, grads
+
+
+# --------------------------------------------------------------------------------------------
+# Inference loop (row L)                       synthesize_expressive_hierarchy.py:36-259
+#                                              (TED-Gesture twin: synthesize_hierarchy.py:36-215)
+# --------------------------------------------------------------------------------------------
+def generate_gestures(variant: str, args, gens: List[SD], audio_sd: SD, word_index, audio: np.ndarray, words,
+                      targets: List[Tensor], vid: int, eps_fn, mel_fn, audio_sr: int = 16000) -> np.ndarray:
+    """Sliding-window autoregressive inference restated over state dicts (eval-mode modules, no fade-out).
+
+    word_index(word) -> token id (lang_model.get_word_index);  eps_fn() -> (1,16) reparameterize noise, called once
+    per generator per window in cascade order (:132-190);  mel_fn(audio) -> (128, frames) log-mel (:50).
+    Pinned by tests/test_oracle_pinned.py against tests/golden/inference.pt, the output of the UNMODIFIED reference loop."""
+    n_frames, n_pre, fps = args.n_poses, args.n_pre_poses, args.motion_resampling_framerate
+    L = len(gens)
+    chans = level_channels(variant)
+    spectrogram = torch.as_tensor(np.asarray(mel_fn(audio), dtype=np.float32))             # :50
+    clip_length = len(audio) / audio_sr                                                    # :43
+    unit_time = n_frames / fps                                                             # :53
+    stride_time = (n_frames - n_pre) / fps                                                 # :54
+    num_subdivision = 1 if clip_length < unit_time else math.ceil((clip_length - unit_time) / stride_time) + 1   # :55-58
+    spec_len = int(round((n_frames / fps * 16000 - 1024) / 512 + 1))                       # data_utils_expressive.py:91-93
+    targets = [t.clone().float() for t in targets]
+    vid_t = torch.tensor([vid], dtype=torch.int64)
+    out_list: List[np.ndarray] = []
+    out_prev = None
+    for i in range(num_subdivision):                                                       # :76
+        start_time = i * stride_time
+        end_time = start_time + unit_time
+        # quirk kept: the window start is scaled by spectrogram.shape[0] (= 128 mel rows), :84
+        a0 = math.floor(start_time / clip_length * spectrogram.shape[0])
+        in_spec = spectrogram[:, a0:a0 + spec_len].unsqueeze(0)                            # :85-87
+        ext = np.zeros(n_frames)                                                           # :101-111
+        frame_duration = (end_time - start_time) / n_frames
+        for w in words:
+            if w[1] >= end_time:
+                break
+            if w[2] <= start_time:
+                continue
+            idx = max(0, int(np.floor((w[1] - start_time) / frame_duration)))
+            ext[idx] = word_index(w[0])
+        in_text = torch.as_tensor(ext.astype(np.int64)).unsqueeze(0)                       # :112-114
+        if i > 0:                                                                          # :117-125 seed frames
+            for k in range(L):
+                targets[k][0, 0:n_pre, :] = out_prev[-n_pre:][:, torch.as_tensor(chans[k])]
+        with torch.no_grad():
+            _, _, _, _, blends = wav_encoder(audio_sd, in_spec, vid_t, L, training=False)  # :130
+            # the per-level targets are independent inputs in window 0 (:36-41), so the levels are chained here directly
+            # (same wiring as cascade(): make_pre_seq of level k from level k-1's output)
+            cmaps = cascade_maps(variant)
+            outs, prev = [], None
+            for k in range(L):                                                             # :132-190
+                pre = make_pre_seq(targets[k], prev, cmaps[k], n_pre)
+                o, _, _, _ = pose_generator(gens[k], pre, in_text, blends[k], vid_t, eps_fn(), args.n_layers, args.hidden_size)
+                outs.append(o)
+                prev = o
+        out_seq = outs[-1][0].numpy().copy()                                               # :192
+        out_prev = torch.as_tensor(out_seq)
+        if out_list:                                                                       # :195-203 cross-fade
+            last = out_list[-1][-n_pre:]
+            out_list[-1] = out_list[-1][:-n_pre]
+            n = len(last)
+            for j in range(n):
+                out_seq[j] = last[j] * (n - j) / (n + 1) + out_seq[j] * (j + 1) / (n + 1)
+        out_list.append(out_seq)
+    return np.vstack(out_list)                                                             # :206

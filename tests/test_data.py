@@ -63,7 +63,8 @@ def test_shard_round_trip_and_collate(tmp_path):
         dur = n_ext / 15
         samples.append(([["hello", 5.0 + 0.2, 5.4], ["world", 5.0 + 1.5, 6.7]], rs.randn(n_ext, 43, 3).astype(np.float32),
                         rs.randn(n_ext, 42, 3).astype(np.float32), rs.randn(int(dur * 16000) - 100 * i).astype(np.float32),
-                        (rs.rand(128, 86) * -80).astype(np.float16), {"vid": f"v{i}", "start_time": 5.0, "end_time": 5.0 + dur}))
+                        (rs.rand(128, 86) * -80).astype(np.float16), {"vid": f"v{i}", "start_time": 5.0, "end_time": 5.0 + dur,
+                                                                     "start_frame_no": np.int64(75 + i), "end_frame_no": np.int64(117 + i)}))   # numpy-typed aux
     data.write_shard(str(tmp_path / "shard0"), samples)
     ds = data.SpeechMotionShardDataset(str(tmp_path / "shard0"), 34, 15)
     ds.set_lang_model(lang)

@@ -175,3 +175,29 @@ def test_train_step(golden_steps, variant):
                         noise_only = tag == "dis" and name in ("pre_conv.0.bias", "pre_conv.3.bias")
                         assert_params_close(sd[name], summ, f"step{step}.{tag}{i}.{name}", lr, step + 1,
                                             1.0 if (noise_only or step > 0) else (0.10 if tag == "audio" else 0.02))
+
+
+def test_inference_loop_vs_reference():
+    """O.generate_gestures (the CPU port behind `bench.py --mode infer --impl reference`) against the output of the
+    UNMODIFIED reference loop scripts/synthesize_expressive_hierarchy.py:36-259 (tests/golden/inference.pt)."""
+    import mel_oracle
+    from ha2g_b200.model.vocab import Vocab
+    from ha2g_b200.synthetic import make_audio
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inference.pt"), weights_only=False)
+    args = make_args("expressive")
+    spk = make_speaker_vocab(g["n_spk"])
+    emb = make_embedding(g["n_words"], 300, 1).numpy()
+    lang = Vocab("words")
+    for w in g["vocab_words"]:
+        lang.index_word(w)
+    dims = (24, 30, 36, 66, 96, 126)
+    gens = [sd_cpu(det_fill(Hierarchical_PoseGenerator(args, d, g["n_words"], 300, emb, z_obj=spk), g["fill_seeds"]["gens"] + i))
+            for i, d in enumerate(dims)]
+    A = sd_cpu(det_fill(Hierarchical_WavEncoder(args, spk, pose_level=6, nOut=32), g["fill_seeds"]["audio"]))
+    audio = make_audio(g["n_samples"], g["audio_seed"]).numpy()
+    targets = [randn((1, 34, d), g["target_seed"], f"t{d}") * 0.1 for d in dims]
+    draws = iter([randn((1, 16), g["eps_seed"], f"eps{i}") for i in range(18)])
+    out = O.generate_gestures("expressive", args, gens, A, lang.get_word_index, audio, g["words"], targets, g["vid"],
+                              lambda: next(draws), lambda a: mel_oracle.extract_melspectrogram(a))
+    assert out.shape == tuple(g["out"].shape)
+    assert_close(torch.from_numpy(out), g["out"], "oracle inference loop", 1e-4)
