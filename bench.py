@@ -123,8 +123,8 @@ def ncu_traffic(kernel_key):
 def launcher_flops(name, a):
     if name in ("ha2g_gemm_f32", "ha2g_gemm"):
         return 2.0 * a[4] * a[5] * a[6]
-    if name == "ha2g_gru_layer_fwd":      # (x, I, ..., gi, y, gates, M, T, H, stream)
-        I, M, T, H = a[1], a[13], a[14], a[15]
+    if name == "ha2g_gru_layer_fwd":      # (x, I, ..., gi, y, gates, M, M_gates, T, H, stream)
+        I, M, T, H = a[1], a[13], a[15], a[16]
         return 2.0 * M * T * 2 * (3 * H * I + 3 * H * H)
     if name == "ha2g_gru_layer_bwd":      # backward = 2x forward GEMM work
         I, M, T, H = a[4], a[23], a[24], a[25]
@@ -171,7 +171,7 @@ def gru_kernel_roofline(dev, M, T=T_FRAMES, H=300, iters=24):
 
     def launch(i):
         gi, y, gates = sets[i % len(sets)]
-        rc = lib.ha2g_gru_seq_fwd_tc2(p(gi), p(w[0]), p(w[1]), p(b[0]), p(b[1]), p(y), p(gates), M, T, H, st)
+        rc = lib.ha2g_gru_seq_fwd_tc2(p(gi), p(w[0]), p(w[1]), p(b[0]), p(b[1]), p(y), p(gates), M, M, T, H, st)
         assert rc is None or rc == 0
     for i in range(4):
         launch(i)

@@ -123,30 +123,41 @@ __global__ void se_fc_bwd_kernel(const float* __restrict__ ds, const float* __re
     }
 }
 // dw2[c][r] += sum_n dz2[n,c] h[n,r];  db2[c] += sum_n dz2[n,c];  dw1[r][c] += sum_n dz1[n,r] gap[n,c];  db1[r] += sum_n dz1[n,r]
-// one thread per (c, r) pair (+ the bias columns), samples summed in index order
+// one thread per (c, r) pair (+ the bias columns), samples summed in index order (4 independent partial chains, combined
+// in a fixed order: deterministic, and the loads of consecutive samples are in flight together)
 __global__ void se_fc_wgrad_kernel(const float* __restrict__ dz2, const float* __restrict__ dz1, const float* __restrict__ hbuf,
                                    const float* __restrict__ gap, float* __restrict__ dw1, float* __restrict__ db1,
                                    float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= C * (R + 1)) return;
     const int c = e / (R + 1), r = e % (R + 1);
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
     if (r == R) {
-        float a = 0.f;
-        for (int n = 0; n < N; ++n) a += dz2[(size_t)n * C + c];
-        db2[c] += a;
-        if (c < R) {
-            float b = 0.f;
-            for (int n = 0; n < N; ++n) b += dz1[(size_t)n * R + c];
-            db1[c] += b;
+        for (int n0 = 0; n0 < N; n0 += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = n0 + k;
+                if (n < N) {
+                    a[k] += dz2[(size_t)n * C + c];
+                    if (c < R) b[k] += dz1[(size_t)n * R + c];
+                }
+            }
         }
+        db2[c] += (a[0] + a[1]) + (a[2] + a[3]);
+        if (c < R) db1[c] += (b[0] + b[1]) + (b[2] + b[3]);
     } else {
-        float a = 0.f, b = 0.f;
-        for (int n = 0; n < N; ++n) {
-            a = fmaf(dz2[(size_t)n * C + c], hbuf[(size_t)n * R + r], a);
-            b = fmaf(dz1[(size_t)n * R + r], gap[(size_t)n * C + c], b);
+        for (int n0 = 0; n0 < N; n0 += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = n0 + k;
+                if (n < N) {
+                    a[k] = fmaf(dz2[(size_t)n * C + c], hbuf[(size_t)n * R + r], a[k]);
+                    b[k] = fmaf(dz1[(size_t)n * R + r], gap[(size_t)n * C + c], b[k]);
+                }
+            }
         }
-        dw2[c * R + r] += a;
-        dw1[r * C + c] += b;
+        dw2[c * R + r] += (a[0] + a[1]) + (a[2] + a[3]);
+        dw1[r * C + c] += (b[0] + b[1]) + (b[2] + b[3]);
     }
 }
 // acc[i] = scale * (part[0][i] + part[1][i] + ...) in index order

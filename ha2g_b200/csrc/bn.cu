@@ -40,13 +40,22 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C
     }
 }
 
-// sums[2C] = sum over the row-chunk partials, in chunk order (deterministic: no atomics anywhere in the reduction)
+// sums[2C] = sum over the row-chunk partials in a FIXED pattern (8 interleaved lanes over the chunks, combined in lane
+// order): deterministic, no atomics anywhere in the reduction.  blockDim = (32 columns, 8 chunk lanes)
 __global__ void bn_combine_kernel(const double* __restrict__ part, int nparts, int C2, double* __restrict__ sums) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C2) return;
+    __shared__ double sh[8][33];
+    const int i = blockIdx.x * 32 + threadIdx.x;
     double t = 0.0;
-    for (int p = 0; p < nparts; ++p) t += part[(size_t)p * C2 + i];
-    sums[i] = t;
+    if (i < C2)
+        for (int p = threadIdx.y; p < nparts; p += 8) t += part[(size_t)p * C2 + i];
+    sh[threadIdx.y][threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < C2) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += sh[k][threadIdx.x];
+        sums[i] = a;
+    }
 }
 
 // mean / invstd from the sums; running-stat update (momentum, unbiased var) as nn.BatchNorm does in train mode
@@ -333,7 +342,7 @@ HA2G_API int ha2g_bn_fwd(const float* x, int64_t rows, int C, int pre_relu, int 
                                                                 0, nullptr, nullptr, part, rows_per);
         else
             bn_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, C, pre_relu, part, rows_per);
-        bn_combine_kernel<<<ha2g_div_up(2 * C, 128), 128, 0, stream>>>(part, nparts, 2 * C, sums_scratch);
+        bn_combine_kernel<<<ha2g_div_up(2 * C, 32), dim3(32, 8), 0, stream>>>(part, nparts, 2 * C, sums_scratch);
         bn_finalize_kernel<<<ha2g_div_up(C, 128), 128, 0, stream>>>(sums_scratch, rows, C, eps, momentum, mean, invstd,
                                                                     running_mean, running_var);
     } else {
@@ -366,7 +375,7 @@ HA2G_API int ha2g_bn_bwd(const float* dy, const float* x, const float* y, int64_
                                                             invstd, part, rows_per);
     else
         bn_bwd_reduce_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, y, rows, C, pre_relu, post_act, mean, invstd, part, rows_per);
-    bn_combine_kernel<<<ha2g_div_up(2 * C, 128), 128, 0, stream>>>(part, nparts, 2 * C, sums_scratch);
+    bn_combine_kernel<<<ha2g_div_up(2 * C, 32), dim3(32, 8), 0, stream>>>(part, nparts, 2 * C, sums_scratch);
     if (bn_vec_ok(C, dy, x, post_act ? (const void*)y : (const void*)x, dx))
         bn_bwd_apply_vec_kernel<<<ha2g_ew_grid(rows * C / 4, 256, 4), 256, 0, stream>>>(
             reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y),

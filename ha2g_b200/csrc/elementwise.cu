@@ -27,6 +27,29 @@ __global__ void col_sum_kernel(const float* __restrict__ x, int rows, int cols, 
         else dst[(size_t)blockIdx.y * cols + c] = t;
     }
 }
+// 32 columns x 32 row lanes, ALL rows: out[c] += sum (4 loads in flight per lane; lanes combined in a fixed order)
+__global__ void __launch_bounds__(1024) col_sum_owner_kernel(const float* __restrict__ x, int rows, int cols, int ld,
+                                                             float* __restrict__ out) {
+    __shared__ float sh[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < cols) {
+        int r = threadIdx.y;
+        for (; r + 96 < rows; r += 128) {
+            s0 += x[(size_t)r * ld + c]; s1 += x[(size_t)(r + 32) * ld + c];
+            s2 += x[(size_t)(r + 64) * ld + c]; s3 += x[(size_t)(r + 96) * ld + c];
+        }
+        for (; r < rows; r += 32) s0 += x[(size_t)r * ld + c];
+    }
+    sh[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t += sh[i][threadIdx.x];
+        out[c] += t;
+    }
+}
 // out[c] += part[0][c] + part[1][c] + ... in index order
 __global__ void col_sum_reduce_kernel(const float* __restrict__ part, int ny, int cols, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,14 +101,21 @@ __global__ void embedding_fwd_kernel(const float* __restrict__ table, const int6
 //   pass 1: head[r] = 1 iff no earlier row has the same index
 //   pass 2: CTA (r, column chunk) of a head row compacts the member rows {r'' >= r : idx[r''] == idx[r]} in order into
 //           shared memory and accumulates dout over them
-__global__ void embedding_heads_kernel(const int64_t* __restrict__ idx, int n, unsigned char* __restrict__ head) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const int64_t me = idx[r];
+__global__ void __launch_bounds__(256) embedding_heads_kernel(const int64_t* __restrict__ idx, int n,
+                                                              unsigned char* __restrict__ head) {
+    __shared__ int64_t tile[256];
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    const int64_t me = r < n ? idx[r] : -1;
     int dup = 0;
+    for (int k0 = 0; k0 <= blockIdx.x * 256; k0 += 256) {   // only rows before this block's last row matter
+        __syncthreads();
+        tile[threadIdx.x] = k0 + threadIdx.x < n ? idx[k0 + threadIdx.x] : -2;
+        __syncthreads();
+        const int lim = min(256, r - k0);                    // compare against rows k < r only
 #pragma unroll 8
-    for (int k = 0; k < r; ++k) dup |= (idx[k] == me) ? 1 : 0;   // no early exit: independent (warp-broadcast) loads
-    head[r] = dup ? 0 : 1;
+        for (int k = 0; k < 256; ++k) dup |= (k < lim && tile[k] == me) ? 1 : 0;
+    }
+    if (r < n) head[r] = dup ? 0 : 1;
 }
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ idx,
                                                             const unsigned char* __restrict__ head,
@@ -319,20 +349,21 @@ __global__ void pre_seq_bwd_kernel(const float* __restrict__ dpre, int w,
 #define EW_LAUNCH(kern, n, ...) \
     do { if ((n) > 0) kern<<<ha2g_ew_grid((n)), 256, 0, stream>>>(__VA_ARGS__); HA2G_RETURN_LAST(); } while (0)
 
-// out[c] += sum_r x[r*ld + c]   (out must be initialised by the caller).  Deterministic: row chunks write partial sums
-// into the scratch arena and a second kernel adds them in chunk order.
+// out[c] += sum_r x[r*ld + c]   (out must be initialised by the caller).  Deterministic: up to 16 384 rows one CTA of
+// 32 x 32 threads owns 32 columns over ALL rows (one launch); beyond that row chunks write partial sums into the scratch
+// arena and a second kernel adds them in chunk order.
 HA2G_API int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return 0;
     int gx = ha2g_div_up(cols, 32);
+    if (rows <= 16384) {
+        col_sum_owner_kernel<<<gx, dim3(32, 32), 0, stream>>>(x, rows, cols, ld, out);
+        HA2G_RETURN_LAST();
+    }
     int want_y = ha2g_div_up(148 * 4, gx);
     int rows_per = ha2g_div_up(rows, want_y);
     if (rows_per < 64) rows_per = 64;
     const int gy = ha2g_div_up(rows, rows_per);
     dim3 grid(gx, gy);
-    if (gy == 1) {
-        col_sum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, cols, ld, out, rows_per, 1);
-        HA2G_RETURN_LAST();
-    }
     float* part = reinterpret_cast<float*>(ha2g_ws((size_t)gy * cols * sizeof(float)));
     if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     col_sum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, cols, ld, part, rows_per, 0);
@@ -360,16 +391,21 @@ HA2G_API int ha2g_embedding_fwd(const float* table, const int64_t* idx, float* o
                                 cudaStream_t stream) {
     EW_LAUNCH(embedding_fwd_kernel, n_idx * dim, table, idx, out, n_idx, dim);
 }
-// dtable[idx[r],:] += dout[r,:]   (dense gradient like nn.Embedding(sparse=False)); deterministic, see the kernels
-HA2G_API int ha2g_embedding_bwd(const float* dout, const int64_t* idx, float* dtable, int64_t n_idx, int dim,
-                                cudaStream_t stream) {
+// head[r] = 1 iff row r is the first occurrence of idx[r] (one byte per row): the work list of ha2g_embedding_bwd.  It
+// depends on the indices only, so the seven text encoders of a step (same token batch) share one call.
+HA2G_API int ha2g_embedding_heads(const int64_t* idx, int64_t n_idx, unsigned char* head, cudaStream_t stream) {
+    if (n_idx <= 0) return 0;
+    embedding_heads_kernel<<<ha2g_div_up(n_idx, 256), 256, 0, stream>>>(idx, (int)n_idx, head);
+    HA2G_RETURN_LAST();
+}
+// dtable[idx[r],:] += dout[r,:]   (dense gradient like nn.Embedding(sparse=False)); deterministic, see the kernels.
+// head: from ha2g_embedding_heads for the same idx.
+HA2G_API int ha2g_embedding_bwd(const float* dout, const int64_t* idx, const unsigned char* head, float* dtable,
+                                int64_t n_idx, int dim, cudaStream_t stream) {
     if (n_idx <= 0 || dim <= 0) return 0;
     const int n = (int)n_idx;
-    if ((size_t)n * sizeof(int) > 200 * 1024) return (int)cudaErrorInvalidValue;
-    unsigned char* head = ha2g_ws((size_t)n);
-    if (head == nullptr) return (int)cudaErrorMemoryAllocation;
-    embedding_heads_kernel<<<ha2g_div_up(n, 128), 128, 0, stream>>>(idx, n, head);
     const size_t smem = (size_t)n * sizeof(int);
+    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(embedding_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

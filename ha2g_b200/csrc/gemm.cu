@@ -205,41 +205,18 @@ HA2G_API int ha2g_gemm_f32(const float* A, const float* B, float* C, const float
 }
 
 // ---- implementation switch ---------------------------------------------------------------------------------------
-// ha2g_gemm / ha2g_gemm_kseg are what the rest of the library calls.  Implementations:
-//   0 "f32"  : exact SIMT kernels above
-//   1 "auto" : (default) bulk-copy-fed tcgen05 bf16x3 GEMM over packed operands (gemm_tc2.cu) for every problem big enough
-//              to amortise the packing pass, SIMT for the small ones
-//   2 "tc"   : register-staged tcgen05 kernel (gemm_tc.cu) everywhere   3 "tc2": packed tcgen05 kernel everywhere
-// HA2G_GEMM_IMPL selects at start-up, ha2g_set_gemm_impl at run time.  HA2G_PRECISION=bf16 (or ha2g_set_gemm_terms(1))
-// switches the tensor-core kernels from the fp32-accurate 3-term split to plain bf16 operands.
-extern "C" int ha2g_gemm_tc_kseg(const float*, const float*, float*, const float*, int, int, int, int, int, int, int, int,
-                                 int, int, int, int, int, cudaStream_t);
+// ha2g_gemm / ha2g_gemm_kseg are what the rest of the library calls: the bulk-copy-fed tcgen05 bf16x3 GEMM over packed
+// operands (gemm_tc2.cu) for every problem big enough to amortise the packing pass, the exact SIMT kernel above for the
+// small ones.  ha2g_set_gemm_impl(0) forces the SIMT kernel everywhere (exact-fp32 parity runs), 3 the tensor-core kernel
+// everywhere; ha2g_set_gemm_terms(1) switches the tensor-core kernel from the fp32-accurate 3-term split to plain bf16.
 extern "C" int ha2g_gemm_tc2(const float*, const float*, float*, const float*, int, int, int, int, int, int, int, int, int,
                              int, int, int, int, int, cudaStream_t);
-#include <cstdlib>
-#include <cstring>
-static int g_gemm_impl = -1;
-static int g_gemm_terms = -1;
-static int gemm_impl() {
-    if (g_gemm_impl < 0) {
-        const char* e = getenv("HA2G_GEMM_IMPL");
-        g_gemm_impl = 1;
-        if (e != nullptr) {
-            if (strcmp(e, "f32") == 0) g_gemm_impl = 0;
-            else if (strcmp(e, "tc") == 0) g_gemm_impl = 2;
-            else if (strcmp(e, "tc2") == 0) g_gemm_impl = 3;
-        }
-    }
-    return g_gemm_impl;
-}
-static int gemm_terms() {
-    if (g_gemm_terms < 0) {
-        const char* e = getenv("HA2G_PRECISION");
-        g_gemm_terms = (e != nullptr && strcmp(e, "bf16") == 0) ? 1 : 3;
-    }
-    return g_gemm_terms;
-}
+static int g_gemm_impl = 1;
+static int g_gemm_terms = 3;
+static int gemm_impl() { return g_gemm_impl; }
+static int gemm_terms() { return g_gemm_terms; }
 HA2G_API int ha2g_set_gemm_impl(int impl) {
+    if (impl != 0 && impl != 1 && impl != 3) return (int)cudaErrorInvalidValue;
     g_gemm_impl = impl;
     return 0;
 }
@@ -255,9 +232,6 @@ HA2G_API int ha2g_gemm_kseg(const float* A, const float* B, float* C, const floa
     if (impl == 3 || (impl == 1 && flops >= 6.0e7 && K >= 32))
         return ha2g_gemm_tc2(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, act, accumulate, split_k, kseg_len,
                              kseg_stride, gemm_terms(), stream);
-    if (impl == 2)
-        return ha2g_gemm_tc_kseg(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, act, accumulate, split_k, kseg_len,
-                                 kseg_stride, stream);
     return ha2g_gemm_f32_kseg(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, act, accumulate, split_k, kseg_len,
                               kseg_stride, stream);
 }

@@ -21,56 +21,24 @@ extern "C" int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* o
 extern "C" int ha2g_gemm_kseg(const float*, const float*, float*, const float*, int, int, int, int, int, int, int,
                                   int, int, int, int, int, int, cudaStream_t);
 
-extern "C" int ha2g_gru_cluster_supported(int H, int* ok);
-extern "C" int ha2g_gru_seq_fwd_cluster(const float*, const float*, const float*, const float*, const float*, float*, float*,
-                                        int, int, int, cudaStream_t);
-extern "C" int ha2g_gru_seq_bwd_cluster(const float*, int, int, const float*, const float*, const float*, const float*,
-                                        float*, float*, int, int, int, cudaStream_t);
 #include <cstdlib>
 #include <cstring>
 
-extern "C" int ha2g_gru_tc_supported(int H, int* ok);
-extern "C" int ha2g_gru_seq_fwd_tc(const float*, const float*, const float*, const float*, const float*, float*, float*, int,
-                                   int, int, cudaStream_t);
+// The recurrences run on the tcgen05 cluster kernels (gru_cluster_tc2.cu forward, gru_cluster_tc2_bwd.cu backward) for
+// every hidden size they can serve (H = 300 generators, H = 64 discriminator); the per-step fp32 kernels of this file
+// are the exact fallback for any other H.
 extern "C" int ha2g_gru_tc2_supported(int H, int* ok);
 extern "C" int ha2g_gru_seq_fwd_tc2(const float*, const float*, const float*, const float*, const float*, float*, float*, int,
-                                    int, int, cudaStream_t);
-// HA2G_GRU_IMPL = step    : per-step kernels of this file
-//               = cluster : persistent cluster kernels, fp32 FMA inner product (gru_cluster.cu)
-//               = tc      : tcgen05 forward recurrence, W_hh slice in shared memory (gru_cluster_tc.cu)
-//               = (unset) : tcgen05 forward recurrence, W_hh slice in tensor memory, bulk-copy h exchange
-//                           (gru_cluster_tc2.cu)
-static bool use_cluster_path(int H) {
-    const char* e = getenv("HA2G_GRU_IMPL");
-    if (e != nullptr && strcmp(e, "step") == 0) return false;
-    int ok = 0;
-    ha2g_gru_cluster_supported(H, &ok);
-    return ok != 0;
-}
-static bool use_tc_recurrence(int H) {
-    const char* e = getenv("HA2G_GRU_IMPL");
-    if (e != nullptr && (strcmp(e, "step") == 0 || strcmp(e, "cluster") == 0)) return false;
-    int ok = 0;
-    ha2g_gru_tc_supported(H, &ok);
-    return ok != 0;
-}
-
+                                    int, int, int, cudaStream_t);
 extern "C" int ha2g_gru_tc2_bwd_supported(int H, int* ok);
 extern "C" int ha2g_gru_seq_bwd_tc2(const float*, int, int, const float*, const float*, const float*, const float*, float*,
                                     float*, int, int, int, cudaStream_t);
-// backward recurrence on tcgen05 (gru_cluster_tc2_bwd.cu) unless HA2G_GRU_IMPL / HA2G_GRU_BWD_IMPL select an older path
 static bool use_tc2_bwd(int H) {
-    const char* e = getenv("HA2G_GRU_IMPL");
-    if (e != nullptr && e[0] != 0) return false;
-    const char* b = getenv("HA2G_GRU_BWD_IMPL");
-    if (b != nullptr && strcmp(b, "cluster") == 0) return false;
     int ok = 0;
     ha2g_gru_tc2_bwd_supported(H, &ok);
     return ok != 0;
 }
 static bool use_tc2_recurrence(int H) {
-    const char* e = getenv("HA2G_GRU_IMPL");
-    if (e != nullptr && e[0] != 0) return false;
     int ok = 0;
     ha2g_gru_tc2_supported(H, &ok);
     return ok != 0;
@@ -88,7 +56,8 @@ __global__ void __launch_bounds__(GR_NT) gru_step_fwd_kernel(const float* __rest
                                                              const float* __restrict__ w_hh_r,
                                                              const float* __restrict__ b_hh_f,
                                                              const float* __restrict__ b_hh_r, float* __restrict__ y,
-                                                             float* __restrict__ gates, int M, int T, int H, int s) {
+                                                             float* __restrict__ gates, int M, int M_gates, int T, int H,
+                                                             int s) {
     __shared__ __align__(16) float Hs[GR_BK][GR_ROWS + 4];
     __shared__ __align__(16) float Ws[GR_BK][3 * GR_HID + 4];
     __shared__ float Gs[GR_ROWS][3 * GR_HID + 1];
@@ -161,7 +130,7 @@ __global__ void __launch_bounds__(GR_NT) gru_step_fwd_kernel(const float* __rest
         float hp = s > 0 ? y[((size_t)gm * T + tp) * 2 * H + dir * H + j] : 0.f;
         float hnew = (1.f - zz) * nn + zz * hp;
         y[row * 2 * H + dir * H + j] = hnew;
-        if (gates != nullptr) {
+        if (gates != nullptr && gm < M_gates) {
             float* gs = gates + (row * 2 + dir) * 4 * H;
             gs[j] = rr; gs[H + j] = zz; gs[2 * H + j] = nn; gs[3 * H + j] = hn;
         }
@@ -207,20 +176,24 @@ __global__ void gru_gates_bwd_kernel(const float* __restrict__ dy, int dy_ld, in
 // scripts/model/hierarchy_net.py:144 generator / :232 discriminator): gi = x W_ih^T + b_ih (two GEMMs),
 // then T fused "h W_hh^T + gates" step launches covering both directions.
 //   x [M,T,I];  w_ih_* [3H,I], w_hh_* [3H,H], b_* [3H] (gate order r,z,n; *_f forward, *_r reverse direction)
-//   gi [M,T,2,3H] scratch/out;  y [M,T,2H] out;  gates [M,T,2,4H] out (nullptr = inference, nothing saved)
+//   gi [M,T,2,3H] scratch/out;  y [M,T,2H] out;  gates [M_gates,T,2,4H] out: saved for the FIRST M_gates batch rows only
+//   (the rows whose backward pass will run; nullptr = inference, nothing saved)
 HA2G_API int ha2g_gru_layer_fwd(const float* x, int I, const float* w_ih_f, const float* w_ih_r, const float* b_ih_f,
                                 const float* b_ih_r, const float* w_hh_f, const float* w_hh_r, const float* b_hh_f,
-                                const float* b_hh_r, float* gi, float* y, float* gates, int M, int T, int H,
+                                const float* b_hh_r, float* gi, float* y, float* gates, int M, int M_gates, int T, int H,
                                 cudaStream_t stream) {
     const int MT = M * T;
-    HA2G_CHECK(ha2g_gemm(x, w_ih_f, gi, b_ih_f, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
-    HA2G_CHECK(ha2g_gemm(x, w_ih_r, gi + 3 * H, b_ih_r, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
-    if (use_tc2_recurrence(H)) return ha2g_gru_seq_fwd_tc2(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, stream);
-    if (use_tc_recurrence(H)) return ha2g_gru_seq_fwd_tc(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, stream);
-    if (use_cluster_path(H)) return ha2g_gru_seq_fwd_cluster(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, stream);
+    if (w_ih_r == w_ih_f + (size_t)3 * H * I && b_ih_r == b_ih_f + 3 * H) {
+        // both directions' input weights are adjacent (one [6H, I] matrix): ONE projection GEMM with N = 6H
+        HA2G_CHECK(ha2g_gemm(x, w_ih_f, gi, b_ih_f, MT, 6 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
+    } else {
+        HA2G_CHECK(ha2g_gemm(x, w_ih_f, gi, b_ih_f, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
+        HA2G_CHECK(ha2g_gemm(x, w_ih_r, gi + 3 * H, b_ih_r, MT, 3 * H, I, I, I, 6 * H, 0, 1, 0, 0, 1, stream));
+    }
+    if (use_tc2_recurrence(H)) return ha2g_gru_seq_fwd_tc2(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, M_gates, T, H, stream);
     dim3 grid(ha2g_div_up(H, GR_HID), ha2g_div_up(M, GR_ROWS), 2);
     for (int s = 0; s < T; ++s) {
-        gru_step_fwd_kernel<<<grid, GR_NT, 0, stream>>>(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, s);
+        gru_step_fwd_kernel<<<grid, GR_NT, 0, stream>>>(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, M_gates, T, H, s);
     }
     HA2G_RETURN_LAST();
 }
@@ -240,12 +213,9 @@ HA2G_API int ha2g_gru_layer_bwd(const float* dy, int dy_ld, int dy_dir_stride, c
     cudaError_t ce = cudaMemsetAsync(dh_rec, 0, sizeof(float) * (size_t)M * 2 * H, stream);
     if (ce != cudaSuccess) return (int)ce;
     const int ew_grid = ha2g_ew_grid((int64_t)M * 2 * H, 256, 1);
-    const bool tc2 = use_tc2_bwd(H);
-    const bool clustered = tc2 || use_cluster_path(H);
-    if (tc2)
+    const bool clustered = use_tc2_bwd(H);
+    if (clustered)
         HA2G_CHECK(ha2g_gru_seq_bwd_tc2(dy, dy_ld, dy_dir_stride, y, gates, w_hh_f, w_hh_r, dgi, dgh, M, T, H, stream));
-    else if (clustered)
-        HA2G_CHECK(ha2g_gru_seq_bwd_cluster(dy, dy_ld, dy_dir_stride, y, gates, w_hh_f, w_hh_r, dgi, dgh, M, T, H, stream));
     for (int s = T - 1; s >= 0 && !clustered; --s) {
         gru_gates_bwd_kernel<<<ew_grid, 256, 0, stream>>>(dy, dy_ld, dy_dir_stride, y, gates, dgi, dgh, dh_rec, M, T, H, s);
         if (s > 0) {

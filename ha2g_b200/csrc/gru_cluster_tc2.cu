@@ -1,9 +1,14 @@
 // Persistent cluster GRU recurrence, second generation (forward) -- the fused GRU kernel of the step.
 //
-// Decomposition as in gru_cluster_tc.cu: an 8-CTA cluster per (direction, 16-row batch chunk); CTA `rank` owns HSP = 40
-// hidden units = 3*HSP gate rows (r | z | n, zero-padded to M = 128) of W_hh for all T steps, and every step computes
-//     gates^T[128 x 16] = W_slice[128 x K] * h_{t-1}^T[K x 16]          (K = 8*HSP = 320, bf16x3 split, fp32 accumulate)
-// on tcgen05.  What changed, each item taken from the phase timing of the first kernel (tools/time_gru_tc.py:
+// Decomposition: an 8-CTA cluster per (direction, NB-row batch chunk), NB = 16 / 32 / 48 chosen from the batch so that the
+// 16 resident clusters cover it in one wave (M <= 128 / <= 256 / larger: the 3B-row cascade of the training step runs at
+// NB = 48); CTA `rank` owns HSP = 40 hidden units = 3*HSP gate rows (r | z | n, zero-padded to M = 128) of W_hh for all T
+// steps, and every step computes
+//     gates^T[128 x NB] = W_slice[128 x K] * h_{t-1}^T[K x NB]          (K = 8*HSP = 320, bf16x3 split, fp32 accumulate)
+// on tcgen05: the same 60 tcgen05.mma per step carry NB columns, the fixed per-step latency (mbarrier wake-ups, TMEM
+// round trip, DSMEM flight) is amortised over NB rows, and with NB > 16 eight epilogue warps (two per TMEM lane quarter,
+// each taking half of the columns) keep the gate math at one 8-unit item per thread.
+// History, each item taken from the phase timing of the first kernel (tools/time_gru_tc.py:
 // 10 600 cycles per step = MMA issue 4 170 + gate math/stores 3 230 + DSMEM push 1 950 + cluster barrier 910):
 //   * W_slice lives in TENSOR MEMORY (tcgen05.st once per layer, 320 columns: hi | lo) and is the MMA's A operand
 //     straight from TMEM.  With A in shared memory every one of the 60 MMAs of a step re-read 4 KB of weights through
@@ -29,11 +34,12 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int CL = 8;          // CTAs per cluster
-constexpr int NB = 16;         // batch rows per cluster task (= UMMA N)
 constexpr int TM = 128;        // UMMA M (gate rows incl. padding)
-constexpr int TNT = 160;       // warp 0: MMA issue + TMEM alloc; warps 1-4: epilogue
-constexpr int TMEM_COLS = 512; // D at columns [0,16), W_slice hi at [32, 32+K/2), lo right after
-constexpr int A_COL = 32;
+constexpr int TMEM_COLS = 512; // D at columns [0,NB), W_slice hi at [64, 64+K/2), lo right after
+constexpr int A_COL = 64;
+// NB = batch rows per cluster task (= UMMA N); epilogue warps: 4 at NB = 16, 8 above (warp 0 issues the MMAs)
+__host__ __device__ constexpr int epi_warps(int NB) { return NB == 16 ? 4 : 8; }
+__host__ __device__ constexpr int block_threads(int NB) { return 32 + 32 * epi_warps(NB); }
 constexpr size_t MIN_SMEM = 120 * 1024;  // > half of the SM's shared memory: one CTA per SM, so the 512-column TMEM
                                          // allocation can never wait on a co-resident CTA of the same cluster
 
@@ -44,6 +50,7 @@ struct Tc2Params {
     float* y;              // [M,T,2H]
     float* gates;          // [M,T,2,4H] or nullptr
     int M, T, H, HSP, n_chunks;
+    int M_gates;           // gates are stored for batch rows < M_gates only (the rows whose BPTT will run)
     long long* dbg;        // optional [T+1][8] clock64 samples of cluster 0 / rank 0 (phase timing), nullptr otherwise
 };
 
@@ -118,40 +125,47 @@ __device__ __forceinline__ void split2g(float a, float b, uint32_t& hi, uint32_t
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
-// shared memory map (bytes): h[2] | staging[2] | G | hown | barriers | tmem slot | W rows (one-time staging)
+// shared memory map (bytes): barriers | tmem slot | { h[2] | G | hown | out staging }, the braces aliasing the one-time
+// fp32 staging of the CTA's W_hh rows (consumed into tensor memory before the first task starts)
 struct Tc2Layout {
     int kc;  // K chunks = CL * HSP / 8
-    size_t b_bytes, slice_bytes, off_stage, off_g, off_hown, off_out, off_bar, off_w, total;
+    size_t b_bytes, slice_bytes, off_h, off_g, off_hown, off_out, off_bar, off_w, total;
     int orow;   // floats per (array, batch row) line of the output staging (HSP + 4: conflict-free 128-bit stores)
-    __host__ __device__ Tc2Layout(int HSP, int H) {
+    __host__ __device__ Tc2Layout(int HSP, int H, int NB) {
         kc = CL * HSP / 8;
         b_bytes = (size_t)kc * 2 * NB * 16;
         slice_bytes = (size_t)(HSP / 8) * 2 * NB * 16;
-        off_stage = 2 * b_bytes;
-        off_g = off_stage + 2 * slice_bytes;
+        off_bar = 0;
+        off_h = 128;
+        off_w = 128;
+        off_g = off_h + 2 * b_bytes;
         off_hown = off_g + (size_t)TM * (NB + 1) * 4;
         off_out = (off_hown + (size_t)HSP * NB * 4 + 15) / 16 * 16;
         orow = HSP + 4;
-        off_bar = off_out + (size_t)5 * NB * orow * 4;   // y | r | z | n | hn lines of one step
-        off_bar = (off_bar + 15) / 16 * 16;
-        off_w = off_bar + 64;
-        total = off_w + (size_t)3 * HSP * H * 4;   // fp32 W_hh rows of this CTA, bulk-copied once per layer
+        const size_t loop_end = off_out + (size_t)5 * NB * orow * 4;   // y | r | z | n | hn lines of one step
+        const size_t w_end = off_w + (size_t)3 * HSP * H * 4;          // fp32 W_hh rows of this CTA, bulk-copied once
+        total = loop_end > w_end ? loop_end : w_end;
+        total = (total + 127) / 128 * 128;
         if (total < MIN_SMEM) total = MIN_SMEM;
     }
 };
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd_tc2_kernel(Tc2Params p) {
+template <int NB>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 1) gru_seq_fwd_tc2_kernel(Tc2Params p) {
+    constexpr int NEW = epi_warps(NB);          // epilogue warps
+    constexpr int TNT = block_threads(NB);
+    constexpr int NET = 32 * NEW;               // epilogue threads
+    constexpr int CPW = NB / (NEW / 4);         // accumulator columns handled per epilogue warp
     extern __shared__ __align__(128) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int dir = cluster_id & 1;
     const int H = p.H, HSP = p.HSP, T = p.T, M = p.M;
-    const Tc2Layout L(HSP, H);
+    const Tc2Layout L(HSP, H, NB);
     const int KC = L.kc;                 // K chunks (K = 8*KC)
     const int CPC = HSP / 8;             // chunks owned per CTA
-    unsigned char* hbuf = smem;                         // [2][KC][2][NB][16 B]
-    unsigned char* stage = smem + L.off_stage;          // [2][CPC][2][NB][16 B]
+    unsigned char* hbuf = smem + L.off_h;               // [2][KC][2][NB][16 B]
     float* G = reinterpret_cast<float*>(smem + L.off_g);         // [TM][NB+1]
     float* hown = reinterpret_cast<float*>(smem + L.off_hown);   // [HSP][NB]
     float* outst = reinterpret_cast<float*>(smem + L.off_out);   // [5][NB][orow]
@@ -171,6 +185,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
     float* __restrict__ g_y = p.y;
     float* __restrict__ g_gates = p.gates;
     long long* g_dbg = p.dbg;
+    const int M_gates = p.M_gates;
     const uint32_t tx_bytes = (uint32_t)(CL * L.slice_bytes);
 
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
@@ -194,10 +209,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
     const uint32_t tmem_ahi = tmem_base + A_COL, tmem_alo = tmem_base + A_COL + (uint32_t)KC * 4;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
-    // epilogue roles: warps 1..4 -> TMEM lane quarter (warp & 3); gate item = (chunk cc of the CTA, batch row b)
-    const int et = tid - 32;                        // 0..127 for epilogue threads
+    // epilogue roles: warp -> TMEM lane quarter (warp & 3) and, with 8 warps, column half (warp - 1) / 4;
+    // gate item = (chunk cc of the CTA, batch row b)
+    const int et = tid - 32;                        // 0..NET-1 for epilogue threads
     const bool is_epi = warp >= 1;
     const int q = warp & 3;
+    const int col0 = is_epi ? ((warp - 1) >> 2) * CPW : 0;   // first accumulator column of this warp
     const int cc = is_epi ? et / NB : 0, bb = is_epi ? et % NB : 0;
     const bool has_item = is_epi && cc < CPC;
 
@@ -227,7 +244,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
     }
     // shared -> TMEM: lane = gate row, 32-bit column c*4+i = the bf16 pair (k = 8c+2i, 8c+2i+1): the A-operand layout of
     // kind::f16 with A in tensor memory
-    if (is_epi) {
+    if (is_epi && warp <= 4) {   // one warp per TMEM lane quarter
         const int row = q * 32 + lane;
         const int g = row / HSP, u = row % HSP, j = j0 + u;
         const bool valid = g < 3 && j < H;
@@ -270,12 +287,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
         const bool okj = has_item && j < H;
         bhr[i] = okj ? b_hh[j] : 0.f; bhz[i] = okj ? b_hh[H + j] : 0.f; bhn[i] = okj ? b_hh[2 * H + j] : 0.f;
     }
-    // copy-out roles (fixed per thread; NB * HSP/4 <= 160 float4 per line group, 128 epilogue threads)
+    // copy-out roles (fixed per thread; NB * HSP/4 <= 2 * NET float4 per line group)
     int co_n = 0, co_rb[2] = {0, 0}, co_f4[2] = {0, 0};
     if (is_epi) {
         const int q4 = HSP / 4;
         for (int k = 0; k < 2; ++k) {
-            const int idx = et + k * 128;
+            const int idx = et + k * NET;
             if (idx < NB * q4) { co_rb[k] = idx / q4; co_f4[k] = idx % q4; co_n = k + 1; }
         }
     }
@@ -356,22 +373,23 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                 mbw(bar_mma, it & 1);
                 if (dbg_on && tid == 32) g_dbg[s * 8 + 2] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                {   // TMEM -> shared: lane (gate row) q*32+lane holds 16 batch columns
-                    uint32_t r[16];
-                    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float* grow = G + (size_t)(q * 32 + lane) * (NB + 1);
+                {   // TMEM -> shared: lane (gate row) q*32+lane, this warp's CPW batch columns, 8 at a time
+                    uint32_t r[CPW];
+                    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) grow[i] = __uint_as_float(r[i]);
+                    for (int c8 = 0; c8 < CPW / 8; ++c8)
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                            : "=r"(r[c8 * 8 + 0]), "=r"(r[c8 * 8 + 1]), "=r"(r[c8 * 8 + 2]), "=r"(r[c8 * 8 + 3]),
+                              "=r"(r[c8 * 8 + 4]), "=r"(r[c8 * 8 + 5]), "=r"(r[c8 * 8 + 6]), "=r"(r[c8 * 8 + 7])
+                            : "r"(taddr + (uint32_t)(c8 * 8)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float* grow = G + (size_t)(q * 32 + lane) * (NB + 1) + col0;
+#pragma unroll
+                    for (int i = 0; i < CPW; ++i) grow[i] = __uint_as_float(r[i]);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps
+                asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");  // the epilogue warps
                 if (dbg_on && tid == 32) g_dbg[s * 8 + 3] = clock64();
                 float hnew[8], sr[8], sz[8], sn[8], shn[8];
 #pragma unroll
@@ -446,7 +464,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                             reinterpret_cast<float4*>(o + 4 * as)[1] = make_float4(shn[4], shn[5], shn[6], shn[7]);
                         }
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");
                     // copy-out: thread -> up to two fixed (batch row, float4) positions of every line group
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
@@ -457,7 +475,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
                                 const size_t row = (size_t)bg * T + t;
                                 const float* src = outst + (size_t)rb * OR + f4 * 4;
                                 *reinterpret_cast<float4*>(g_y + row * 2 * H + dir * H + jg) = *reinterpret_cast<const float4*>(src);
-                                if (narr == 5) {
+                                if (narr == 5 && bg < M_gates) {
                                     float* gd = g_gates + (row * 2 + dir) * 4 * H + jg;
 #pragma unroll
                                     for (int a = 1; a < 5; ++a)
@@ -482,44 +500,66 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_fwd
 
 }  // namespace
 
+// batch rows per cluster task for a batch of M rows: the smallest NB whose chunks fit the 16 resident clusters in one wave
+static int pick_nb(int M) { return M <= 128 ? 16 : (M <= 256 ? 32 : 48); }
+
 // 1 through *ok if the second-generation tensor-core recurrence can serve hidden size H (gate rows 3*HSP <= 128, the
-// W_hh slice fits 480 TMEM columns, one 8-unit item per epilogue thread).
+// W_hh slice fits the TMEM columns behind the accumulator, one 8-unit item per epilogue thread at every NB).
 HA2G_API int ha2g_gru_tc2_supported(int H, int* ok) {
     const int HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
-    const Tc2Layout L(HSP, H);
     const int kc = CL * HSP / 8;
-    *ok = (3 * HSP <= TM && (HSP / 8) * NB <= 128 && kc % 2 == 0 && A_COL + kc * 8 <= TMEM_COLS && H % 4 == 0 && L.total <= 227 * 1024) ? 1 : 0;
+    bool good = 3 * HSP <= TM && kc % 2 == 0 && A_COL + kc * 8 <= TMEM_COLS && H % 4 == 0;
+    for (int nb = 16; nb <= 48 && good; nb += 16) {
+        const Tc2Layout L(HSP, H, nb);
+        good = (HSP / 8) * nb <= 32 * epi_warps(nb) && nb * (HSP / 4) <= 2 * 32 * epi_warps(nb) && L.total <= 227 * 1024;
+    }
+    *ok = good ? 1 : 0;
     return 0;
 }
 
-extern "C" int ha2g_gru_seq_fwd_tc2_dbg(const float*, const float*, const float*, const float*, const float*, float*, float*,
-                                        int, int, int, long long*, cudaStream_t);
-// All T steps of one bidirectional layer, forward, on tcgen05 with W_hh resident in tensor memory (see the file header).
-// gi must hold x W_ih^T + b_ih.  Replaces the recurrence of nn.GRU at scripts/model/hierarchy_net.py:144 / :232.
-HA2G_API int ha2g_gru_seq_fwd_tc2(const float* gi, const float* w_hh_f, const float* w_hh_r, const float* b_hh_f,
-                                  const float* b_hh_r, float* y, float* gates, int M, int T, int H, cudaStream_t stream) {
-    return ha2g_gru_seq_fwd_tc2_dbg(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, T, H, nullptr, stream);
+template <int NB>
+static int launch_tc2(Tc2Params& p, cudaStream_t stream) {
+    p.n_chunks = (p.M + NB - 1) / NB;
+    const Tc2Layout L(p.HSP, p.H, NB);
+    cudaError_t e = cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) return (int)e;
+    int clusters = 2 * p.n_chunks;
+    if (clusters > 16) clusters = 16;
+    gru_seq_fwd_tc2_kernel<NB><<<clusters * CL, block_threads(NB), L.total, stream>>>(p);
+    HA2G_RETURN_LAST();
 }
 
-// Same, with an optional device buffer dbg [T+1][8] of clock64() samples (cluster 0, rank 0) for phase timing:
+extern "C" int ha2g_gru_seq_fwd_tc2_dbg(const float*, const float*, const float*, const float*, const float*, float*, float*,
+                                        int, int, int, int, int, long long*, cudaStream_t);
+// All T steps of one bidirectional layer, forward, on tcgen05 with W_hh resident in tensor memory (see the file header).
+// gi must hold x W_ih^T + b_ih.  gates (nullable) receives r | z | n | hn for the batch rows < M_gates only (the rows
+// whose backward pass will run; M_gates = M saves all).  Replaces the recurrence of nn.GRU at
+// scripts/model/hierarchy_net.py:144 / :232.
+HA2G_API int ha2g_gru_seq_fwd_tc2(const float* gi, const float* w_hh_f, const float* w_hh_r, const float* b_hh_f,
+                                  const float* b_hh_r, float* y, float* gates, int M, int M_gates, int T, int H,
+                                  cudaStream_t stream) {
+    return ha2g_gru_seq_fwd_tc2_dbg(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, M_gates, T, H, 0, nullptr, stream);
+}
+
+// Same, with an explicit rows-per-cluster choice (nb = 16 / 32 / 48; 0 = automatic) and an optional device buffer dbg
+// [T+1][8] of clock64() samples (cluster 0, rank 0) for phase timing:
 // 7 = MMA thread reaches the h-arrival wait, 0 = h arrived / MMA issue starts, 1 = MMAs issued + committed,
 // 2 = epilogue woken by the commit, 3 = accumulator transposed through shared memory, 4 = gate math done,
-// 5 = h_t bulk copies issued, 6 = y / gates stored; row T: 0 = kernel entry, 1 = W_hh rows in shared memory,
+// 5 = h_t pushed to the peers, 6 = y / gates stored; row T: 0 = kernel entry, 1 = W_hh rows in shared memory,
 // 2 = W_hh in tensor memory, 3 = time loop starts, 4 = time loop done.
 HA2G_API int ha2g_gru_seq_fwd_tc2_dbg(const float* gi, const float* w_hh_f, const float* w_hh_r, const float* b_hh_f,
-                                      const float* b_hh_r, float* y, float* gates, int M, int T, int H, long long* dbg,
-                                      cudaStream_t stream) {
+                                      const float* b_hh_r, float* y, float* gates, int M, int M_gates, int T, int H, int nb,
+                                      long long* dbg, cudaStream_t stream) {
+    if (M <= 0 || T <= 0) return 0;
     Tc2Params p{};
     p.dbg = dbg;
     p.gi = gi; p.w_hh[0] = w_hh_f; p.w_hh[1] = w_hh_r; p.b_hh[0] = b_hh_f; p.b_hh[1] = b_hh_r;
     p.y = y; p.gates = gates; p.M = M; p.T = T; p.H = H;
+    p.M_gates = gates != nullptr ? (M_gates < M ? M_gates : M) : 0;
     p.HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
-    p.n_chunks = (M + NB - 1) / NB;
-    const Tc2Layout L(p.HSP, H);
-    cudaError_t e = cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-    if (e != cudaSuccess) return (int)e;
-    int clusters = 2 * p.n_chunks;
-    if (clusters > 16) clusters = 16;
-    gru_seq_fwd_tc2_kernel<<<clusters * CL, TNT, L.total, stream>>>(p);
-    HA2G_RETURN_LAST();
+    if (nb == 0) nb = pick_nb(M);
+    if (nb == 16) return launch_tc2<16>(p, stream);
+    if (nb == 32) return launch_tc2<32>(p, stream);
+    if (nb == 48) return launch_tc2<48>(p, stream);
+    return (int)cudaErrorInvalidValue;
 }

@@ -43,6 +43,76 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+# ------------------------------------------------------------------------------------------------
+# ride-along rows: no-grad companion passes batched INTO the differentiated pass
+# ------------------------------------------------------------------------------------------------
+# The training step runs the generator cascade three times on the same weights: once with gradient (G step) and twice
+# detached (discriminator step, mismatched-speaker pass).  Instead of three cascades -- or one with-grad plus one 2B-row
+# no-grad cascade -- the row-wise ops below can carry the detached rows ALONG with the differentiated ones: while
+# ``ride_along(m)`` is active, every batch-leading tensor of B rows handed to them is the HEAD of a contiguous buffer of
+# m*B rows; forward kernels run over all m*B rows (one launch, m x the rows per GEMM / GRU step), outputs are allocated
+# m*B rows long and returned as their B-row head, and autograd only ever sees the heads: saved tensors, gate buffers and
+# every backward kernel cover B rows.  ``ride_pack`` builds such buffers, ``ride_tails`` reads the companions' rows back.
+_ride = {"mult": 1}
+
+
+class ride_along:
+    def __init__(self, mult: int):
+        self.mult, self.prev = int(mult), 1
+
+    def __enter__(self):
+        self.prev, _ride["mult"] = _ride["mult"], self.mult
+        return self
+
+    def __exit__(self, *exc):
+        _ride["mult"] = self.prev
+        return False
+
+
+def _fv(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The whole ride-along buffer behind a head view (identity when no companions ride along)."""
+    m = _ride["mult"]
+    if m == 1 or t is None:
+        return t
+    if not t.is_contiguous():
+        raise RuntimeError("ride-along tensors must be contiguous heads of their buffers")
+    return torch.as_strided(t, (t.shape[0] * m, *t.shape[1:]), t.stride(), t.storage_offset())   # bounds-checked
+
+
+def _alloc(shape, device, dtype=torch.float32):
+    """-> (full buffer with mult x the leading rows, its head view of `shape`)."""
+    m = _ride["mult"]
+    full = torch.empty((shape[0] * m, *shape[1:]), device=device, dtype=dtype)
+    return full, (full if m == 1 else full[:shape[0]])
+
+
+class _RidePackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, head, *tails):
+        full = torch.cat([head, *tails], dim=0)
+        return full[:head.shape[0]]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g,) + (None,) * (len(ctx.needs_input_grad) - 1)
+
+
+def ride_pack(head: torch.Tensor, tails: Sequence[torch.Tensor]) -> torch.Tensor:
+    """[head; tails...] stacked along the batch axis in one buffer, returned as its head (gradient flows to `head` only)."""
+    tails = [t.detach() for t in tails]
+    if head.requires_grad and torch.is_grad_enabled():
+        return _RidePackFn.apply(head, *tails)
+    return torch.cat([head, *tails], dim=0)[:head.shape[0]]
+
+
+def ride_tails(head: torch.Tensor, mult: int) -> List[torch.Tensor]:
+    """The companions' rows of a ride-along result: mult-1 detached [B, ...] views."""
+    B = head.shape[0]
+    h = head.detach()
+    full = torch.as_strided(h, (B * mult, *h.shape[1:]), h.stride(), h.storage_offset())
+    return [full[k * B:(k + 1) * B] for k in range(1, mult)]
+
+
 _prof = {"on": False, "only": None, "flops_fn": None, "recs": {}}
 
 
@@ -100,8 +170,8 @@ _config = {"gemm_impl": "auto", "precision": "fp32x3"}
 
 def set_gemm_impl(impl: str):
     """'auto' (default): packed tcgen05 bf16x3 GEMM for problems big enough to amortise packing, exact fp32 SIMT for
-    the small ones; 'f32': SIMT only; 'tc': register-staged tcgen05 kernel everywhere; 'tc2': packed kernel everywhere."""
-    lib.ha2g_set_gemm_impl({"f32": 0, "auto": 1, "tc": 2, "tc2": 3}[impl])
+    the small ones; 'f32': SIMT only; 'tc2': packed kernel everywhere."""
+    lib.ha2g_set_gemm_impl({"f32": 0, "auto": 1, "tc2": 3}[impl])
     _config["gemm_impl"] = impl
 
 
@@ -113,8 +183,7 @@ def set_precision(mode: str):
 
 def config_signature() -> tuple:
     """Kernel-selection switches that get baked into a captured CUDA graph (graph_step keys its cache on them)."""
-    return (_config["gemm_impl"], _config["precision"], os.environ.get("HA2G_GRU_IMPL", ""),
-            os.environ.get("HA2G_GRU_BWD_IMPL", ""))
+    return (_config["gemm_impl"], _config["precision"])
 
 
 def profiling() -> bool:
@@ -145,8 +214,8 @@ class _LinearFn(torch.autograd.Function):
         _chk(x2, w, b)
         R, K = x2.shape
         N = w.shape[0]
-        y = torch.empty((R, N), device=x.device, dtype=torch.float32)
-        gemm(x2, w, y, b, R, N, K, K, K, N, 0, 1, act, 0, 1)
+        yf, y = _alloc((R, N), x.device)
+        gemm(_fv(x2), w, yf, b, yf.shape[0], N, K, K, K, N, 0, 1, act, 0, 1)
         ctx.act = act
         ctx.has_bias = b is not None
         ctx.xshape = x.shape
@@ -189,8 +258,8 @@ class _ActFn(torch.autograd.Function):
     def forward(ctx, x, act):
         x = _c(x)
         _chk(x)
-        y = torch.empty_like(x)
-        _call("ha2g_act_fwd", _p(x), _p(y), x.numel(), act, _st())
+        yf, y = _alloc(x.shape, x.device)
+        _call("ha2g_act_fwd", _p(x), _p(yf), yf.numel(), act, _st())
         ctx.act = act
         ctx.save_for_backward(y)
         return y
@@ -215,8 +284,9 @@ class _AddActFn(torch.autograd.Function):
     def forward(ctx, a, b, act):
         a, b = _c(a), _c(b)
         _chk(a, b)
-        y = torch.empty_like(a)
-        _call("ha2g_add_act_fwd", _p(a), _p(b), _p(y), a.numel(), act, _st())
+        _fv(a), _fv(b)   # (bounds check: both are heads of ride-along buffers)
+        yf, y = _alloc(a.shape, a.device)
+        _call("ha2g_add_act_fwd", _p(a), _p(b), _p(yf), yf.numel(), act, _st())
         ctx.act = act
         ctx.save_for_backward(y)
         return y
@@ -264,8 +334,10 @@ class _DropoutFn(torch.autograd.Function):
     def forward(ctx, x, p, call_id):
         x = _c(x)
         _chk(x)
-        y = torch.empty_like(x)
-        _call("ha2g_dropout", _p(x), _p(y), x.numel(), p, _p(_rng.dropout_state(x.device)), call_id, _st())
+        _fv(x)
+        yf, y = _alloc(x.shape, x.device)
+        # the mask is indexed by element: the head's elements come first, so backward regenerates exactly their mask
+        _call("ha2g_dropout", _p(x), _p(yf), yf.numel(), p, _p(_rng.dropout_state(x.device)), call_id, _st())
         ctx.cfg = (p, call_id)
         return y
 
@@ -285,6 +357,8 @@ def dropout(x, p: float, training: bool):
         return x
     if _rng.fused_dropout():
         return _DropoutFn.apply(x, float(p), _rng.next_call_id())
+    if _ride["mult"] != 1:
+        raise RuntimeError("injected dropout masks cannot be combined with ride-along rows")
     mask = _rng.dropout_mask(x.shape, p, x.device)
     return _MulMaskFn.apply(x, mask, 1.0 / (1.0 - p))
 
@@ -297,8 +371,9 @@ class _EmbeddingFn(torch.autograd.Function):
         if idx.dtype != torch.int64 or not idx.is_cuda:
             raise RuntimeError("embedding indices must be CUDA int64")
         dim = table.shape[1]
-        out = torch.empty((*idx.shape, dim), device=table.device, dtype=torch.float32)
-        _call("ha2g_embedding_fwd", _p(table), _p(idx), _p(out), idx.numel(), dim, _st())
+        idxf = _fv(idx)
+        outf, out = _alloc((*idx.shape, dim), table.device)
+        _call("ha2g_embedding_fwd", _p(table), _p(idxf), _p(outf), idxf.numel(), dim, _st())
         ctx.save_for_backward(idx)
         ctx.tshape = table.shape
         return out
@@ -308,8 +383,28 @@ class _EmbeddingFn(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         dout = _c(dout)
         dt = torch.zeros(ctx.tshape, device=dout.device, dtype=torch.float32)
-        _call("ha2g_embedding_bwd", _p(dout), _p(idx), _p(dt), idx.numel(), ctx.tshape[1], _st())
+        _call("ha2g_embedding_bwd", _p(dout), _p(idx), _p(_embedding_heads(idx)), _p(dt), idx.numel(), ctx.tshape[1], _st())
         return dt, None
+
+
+_heads_cache = {}
+
+
+def _embedding_heads(idx: torch.Tensor) -> torch.Tensor:
+    """First-occurrence flags of an index tensor (the work list of the deterministic scatter-add).  All text encoders of
+    a step see the same token batch, so the flags are computed once per (tensor, version) and shared; the cache is
+    cleared at every step start (rng.begin_step)."""
+    key = (idx.data_ptr(), idx._version, idx.numel(), idx.device)
+    hit = _heads_cache.get(key)
+    if hit is None:
+        head = torch.empty((idx.numel(),), dtype=torch.uint8, device=idx.device)
+        _call("ha2g_embedding_heads", _p(idx), idx.numel(), _p(head), _st())
+        hit = _heads_cache[key] = (head, idx)   # holding idx keeps its address from being recycled under the key
+    return hit[0]
+
+
+def clear_step_caches():
+    _heads_cache.clear()
 
 
 def embedding(table, idx):
@@ -321,8 +416,9 @@ class _ReparamFn(torch.autograd.Function):
     def forward(ctx, mu, logvar, eps):
         mu, logvar, eps = _c(mu), _c(logvar), _c(eps)
         _chk(mu, logvar, eps)
-        z = torch.empty_like(mu)
-        _call("ha2g_reparam_fwd", _p(mu), _p(logvar), _p(eps), _p(z), mu.numel(), _st())
+        _fv(mu), _fv(logvar), _fv(eps)
+        zf, z = _alloc(mu.shape, mu.device)
+        _call("ha2g_reparam_fwd", _p(mu), _p(logvar), _p(eps), _p(zf), zf.numel(), _st())
         ctx.save_for_backward(logvar, eps)
         return z
 
@@ -354,10 +450,11 @@ class _ConcatSeqFn(torch.autograd.Function):
         B, T, dp = pre.shape
         widths = [dp, audio.shape[2], text.shape[2], z.shape[1]]
         I = sum(widths)
-        x = torch.empty((B, T, I), device=pre.device, dtype=torch.float32)
+        _fv(pre), _fv(audio), _fv(text), _fv(z)
+        xf, x = _alloc((B, T, I), pre.device)
         off = 0
         for src, w, div in ((pre, widths[0], 1), (audio, widths[1], 1), (text, widths[2], 1), (z, widths[3], T)):
-            _call("ha2g_copy_cols", _p(src), w, 0, div, _p(x), I, off, 1, B * T, w, 0, _st())
+            _call("ha2g_copy_cols", _p(src), w, 0, div, _p(xf), I, off, 1, xf.shape[0] * T, w, 0, _st())
             off += w
         ctx.widths, ctx.BT = widths, (B, T)
         return x
@@ -402,6 +499,8 @@ class _BiGRUFn(torch.autograd.Function):
         x = _c(x)
         _chk(x, *weights)
         M, T, _ = x.shape
+        _fv(x)
+        MF = M * _ride["mult"]   # rows the forward kernels process: the head's M rows + the ride-along companions
         need_grad = any(ctx.needs_input_grad)  # (grad mode is off inside Function.forward)
         saved: List[torch.Tensor] = []
         masks = []
@@ -409,29 +508,32 @@ class _BiGRUFn(torch.autograd.Function):
         for l in range(L):
             w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = weights[8 * l:8 * l + 8]
             I = cur.shape[2]
-            gi = torch.empty((M, T, 6 * H), device=x.device, dtype=torch.float32)
-            y = torch.empty((M, T, 2 * H), device=x.device, dtype=torch.float32)
+            gi = torch.empty((MF, T, 6 * H), device=x.device, dtype=torch.float32)
+            yf, y = _alloc((M, T, 2 * H), x.device)
+            # the gates are saved for the head rows only: the companions are never differentiated
             gates = torch.empty((M, T, 8 * H), device=x.device, dtype=torch.float32) if need_grad else None
             _call("ha2g_gru_layer_fwd", _p(cur), I, _p(w_ih), _p(w_ih_r), _p(b_ih), _p(b_ih_r), _p(w_hh), _p(w_hh_r),
-                  _p(b_hh), _p(b_hh_r), _p(gi), _p(y), _p(gates), M, T, H, _st())
+                  _p(b_hh), _p(b_hh_r), _p(gi), _p(yf), _p(gates), MF, M, T, H, _st())
             if need_grad:
                 saved += [cur, y, gates]
             nxt = y
             mask = None
             if l < L - 1 and training and p > 0.0 and _rng.dropout_enabled():
-                nxt = torch.empty_like(y)
+                nf, nxt = _alloc((M, T, 2 * H), x.device)
                 if _rng.fused_dropout():
                     mask = _rng.next_call_id()   # the mask is regenerated from this id in backward
-                    _call("ha2g_dropout", _p(y), _p(nxt), y.numel(), float(p), _p(_rng.dropout_state(y.device)), mask, _st())
+                    _call("ha2g_dropout", _p(yf), _p(nf), yf.numel(), float(p), _p(_rng.dropout_state(y.device)), mask, _st())
                 else:
+                    if MF != M:
+                        raise RuntimeError("injected dropout masks cannot be combined with ride-along rows")
                     mask = _rng.dropout_mask(y.shape, p, y.device)
                     _call("ha2g_mul_mask", _p(y), _p(mask), 1.0 / (1.0 - p), _p(nxt), y.numel(), _st())
             masks.append(mask)
             cur = nxt
         if sum_dirs:
-            out = torch.empty((M, T, H), device=x.device, dtype=torch.float32)
-            _call("ha2g_copy_cols", _p(cur), 2 * H, 0, 1, _p(out), H, 0, 1, M * T, H, 0, _st())
-            _call("ha2g_copy_cols", _p(cur), 2 * H, H, 1, _p(out), H, 0, 1, M * T, H, 1, _st())
+            of, out = _alloc((M, T, H), x.device)
+            _call("ha2g_copy_cols", _p(cur), 2 * H, 0, 1, _p(of), H, 0, 1, MF * T, H, 0, _st())
+            _call("ha2g_copy_cols", _p(cur), 2 * H, H, 1, _p(of), H, 0, 1, MF * T, H, 1, _st())
         else:
             out = cur
         ctx.cfg = (H, L, p, sum_dirs, M, T)
@@ -528,8 +630,9 @@ class _ShiftConcatFn(torch.autograd.Function):
         x = _c(x)
         _chk(x)
         B, T, C = x.shape
-        out = torch.empty((B, T, 2 * C), device=x.device, dtype=torch.float32)
-        _call("ha2g_shift_concat_fwd", _p(x), _p(out), B, T, C, d, _st())
+        _fv(x)
+        of, out = _alloc((B, T, 2 * C), x.device)
+        _call("ha2g_shift_concat_fwd", _p(x), _p(of), of.shape[0], T, C, d, _st())
         ctx.d = d
         return out
 
@@ -566,12 +669,14 @@ class _PreSeqFn(torch.autograd.Function):
         target_k = _c(target_k)
         _chk(target_k, prev_out)
         B, T, d = target_k.shape
-        pre = torch.empty((B, T, d + 1), device=target_k.device, dtype=torch.float32)
+        _fv(target_k)
+        pf, pre = _alloc((B, T, d + 1), target_k.device)
         dp = 0
         if prev_out is not None:
             prev_out = _c(prev_out)
+            _fv(prev_out)
             dp = prev_out.shape[2]
-        _call("ha2g_pre_seq_fwd", _p(target_k), _p(prev_out), dp, _p(slot_src), _p(pre), B, T, d, n_pre, _st())
+        _call("ha2g_pre_seq_fwd", _p(target_k), _p(prev_out), dp, _p(slot_src), _p(pf), pf.shape[0], T, d, n_pre, _st())
         ctx.cfg = (B, T, d, dp, n_pre)
         ctx.src_slot = src_slot
         return pre

@@ -11,8 +11,9 @@ mechanical and result-preserving:
     computes then discards those gradients: dis_optimizer.zero_grad() precedes the next use);
   * loss terms are back-propagated as several roots with constant weights instead of being summed into
     one scalar first (identical gradients, no scalar arithmetic kernels);
-  * when both exist, those two no-grad cascades run as ONE cascade over 2B rows (``HA2G_BATCH_PASSES=0`` separates
-    them again); the random draws are made up front in the reference's order;
+  * those no-grad cascades ride along with the differentiated cascade as extra batch rows: ONE cascade over 3B rows whose
+    autograd graph covers B of them (``ops.ride_along``; ``HA2G_BATCH_PASSES=0`` separates the passes again); the random
+    draws are made up front in the reference's order;
   * all ``.item()`` reads are packed into a single device->host copy at the end of the step;
   * after two eager calls per (modules, shapes, mode) signature the whole step -- forward, both backwards, the
     gradient all-reduce and the eight Adam updates, ~7 600 kernel launches -- is captured into ONE CUDA graph
@@ -28,7 +29,7 @@ import torch
 
 import os
 
-from .. import cascade, dp, graph_step, ops_loss, rng
+from .. import cascade, dp, graph_step, ops, ops_loss, rng
 from ..optim import fused_adam_step, zero_grad
 
 _BATCH_PASSES = os.environ.get("HA2G_BATCH_PASSES", "1") != "0"
@@ -89,32 +90,46 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
         raise NotImplementedError("z_type='random' is not on the hierarchy configs' path")
 
     # The two cascades whose outputs the reference detaches -- the discriminator-step pass and the mismatched-speaker
-    # pass of the diversity loss -- depend only on the (unchanged) generators, so they run as ONE no-grad cascade over
-    # 2B rows: half the launches, twice the rows per GEMM.  The draws are made up front in the reference's order
-    # (D-pass noise x L, G-pass noise x L, randperm, mismatched-pass noise x L).
-    batched = gan_on and use_reg and _BATCH_PASSES
-    eps_g = out_r_last = z_context_rand = None
-    if batched:
-        eps_d = [rng.randn((B, 16), dev) for _ in range(L)]
+    # pass of the diversity loss -- depend only on the (unchanged) generators, so they RIDE ALONG with the differentiated
+    # G-step cascade as extra batch rows (ops.ride_along): ONE cascade over 3B rows, a third of the launches, three times
+    # the rows per GEMM / GRU step, while autograd, the saved activations and every backward kernel only see the B rows
+    # of the G-step pass.  The draws are made up front in the reference's order (D-pass noise x L, G-pass noise x L,
+    # randperm, mismatched-pass noise x L).
+    tails = (["d"] if gan_on else []) + (["r"] if use_reg else [])
+    ride = _BATCH_PASSES and len(tails) > 0 and rng.fused_dropout()
+    eps_g = out_r_last = z_context_rand = out_d_last = ride_result = None
+    if ride:
+        eps_d = [rng.randn((B, 16), dev) for _ in range(L)] if gan_on else None
         eps_g = [rng.randn((B, 16), dev) for _ in range(L)]
-        rand_vids = vid_indices[rng.randperm(B, vid_indices.device)]
-        eps_r = [rng.randn((B, 16), dev) for _ in range(L)]
+        rand_vids = vid_indices[rng.randperm(B, vid_indices.device)] if use_reg else None
+        eps_r = [rng.randn((B, 16), dev) for _ in range(L)] if use_reg else None
+        m = 1 + len(tails)
+        per_tail = lambda d_val, r_val: [d_val if t == "d" else r_val for t in tails]
+        targets_p = [ops.ride_pack(t, per_tail(t, t)) for t in targets]
+        text_p = ops.ride_pack(in_text_padded, per_tail(in_text_padded, in_text_padded))
+        blends_p = [ops.ride_pack(f, per_tail(f, f)) for f in linear_blend_feat]
+        vid_p = ops.ride_pack(vid_indices, per_tail(vid_indices, rand_vids))
+        eps_p = [ops.ride_pack(eps_g[k], per_tail(eps_d[k] if gan_on else None, eps_r[k] if use_reg else None))
+                 for k in range(L)]
+        with ops.ride_along(m):
+            outs, (z_context, z_mu, z_logvar) = cascade.run_cascade(variant, gens, targets_p, text_p, blends_p, vid_p,
+                                                                    n_pre, eps=eps_p)
+        out_tails, z_tails = ops.ride_tails(outs[-1], m), ops.ride_tails(z_context, m)
+        if gan_on:
+            out_d_last = out_tails[tails.index("d")]
+        if use_reg:
+            out_r_last, z_context_rand = out_tails[tails.index("r")], z_tails[tails.index("r")]
+        ride_result = (outs, z_context, z_mu, z_logvar)
 
     # ------------------------------------------------------------------ train D
     if gan_on:
         zero_grad(dis_optimizer)
-        with torch.no_grad():
-            if batched:
-                two = lambda t: torch.cat([t, t])
-                outs2, (z2, _, _) = cascade.run_cascade(
-                    variant, gens, [two(t) for t in targets], two(in_text_padded), [two(f.detach()) for f in linear_blend_feat],
-                    torch.cat([vid_indices, rand_vids]), n_pre, eps=[torch.cat([d, r]) for d, r in zip(eps_d, eps_r)])
-                outs_d = [outs2[-1][:B]]
-                out_r_last, z_context_rand = outs2[-1][B:], z2[B:]
-            else:
+        if not ride:
+            with torch.no_grad():
                 outs_d, _ = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat, vid_indices, n_pre)
+            out_d_last = outs_d[-1]
         dis_real = discriminator(target, in_text_padded)
-        dis_fake = discriminator(outs_d[-1].detach(), in_text_padded)
+        dis_fake = discriminator(out_d_last.detach(), in_text_padded)
         l_real = ops_loss.neg_mean_log(dis_real)
         l_fake = ops_loss.neg_mean_log1m(dis_fake)
         one = _w(1.0, target)
@@ -145,8 +160,11 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
         add("c_neg", ops_loss.contrastive(tf, feat_low.reshape(-1, feat_low.shape[2]), variant),
             -args.loss_contrastive_neg_weight)
 
-    outs, (z_context, z_mu, z_logvar) = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat,
-                                                            vid_indices, n_pre, eps=eps_g)
+    if ride:
+        outs, z_context, z_mu, z_logvar = ride_result
+    else:
+        outs, (z_context, z_mu, z_logvar) = cascade.run_cascade(variant, gens, targets, in_text_padded, linear_blend_feat,
+                                                                vid_indices, n_pre)
     out_dir_vec = outs[-1]
     for k, (o, t) in enumerate(zip(outs, targets)):
         add(f"huber{k}", ops_loss.huber(o, t, 0.1), args.loss_regression_weight)
@@ -156,7 +174,7 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
     add("gen", ops_loss.neg_mean_log(dis_output), args.loss_gan_weight if epoch > warm_up_epochs else 0.0)
 
     if use_reg:
-        if not batched:
+        if not ride:
             rand_idx = rng.randperm(vid_indices.shape[0], vid_indices.device)
             rand_vids = vid_indices[rand_idx]
             with torch.no_grad():

@@ -118,3 +118,87 @@ def test_reductions_bit_reproducible():
     assert torch.equal(es[0], es[1]) and torch.equal(es[0], es[2])
     ref = torch.zeros(500, 300, dtype=torch.float64, device=DEV).index_add_(0, idx, ge.double())
     assert_close(es[0], ref, "embedding scatter-add", 1e-5)
+
+
+@pytest.mark.parametrize("variant", ["expressive", "gesture"])
+def test_contrastive_n4352_vs_fp64(variant):
+    """SoftmaxContrastiveLoss at the benchmark size N = B*34 = 4352 (train_hierarchy.py:54-68 / ..._expressive.py:108-121):
+    streaming CUDA kernels vs the reference's materialised N x N x 32 formulation evaluated in fp64 (on the device: 4.8 GB).
+    Text-side rows come from the real TextEncoderTCN on a PAD-dominated synthetic batch (many near-identical rows)."""
+    from ha2g_b200 import ops_loss
+    from ha2g_b200.constants import make_args
+    from ha2g_b200.model.hierarchy_net import TextEncoderTCN
+    from ha2g_b200.synthetic import det_fill, make_batch, make_embedding
+    torch.manual_seed(1)
+    B = 128
+    args = make_args("expressive")
+    T = det_fill(TextEncoderTCN(args, 60, 300, pre_trained_embedding=make_embedding(60, 300, 1).numpy(), dropout=0.3), 32).to(DEV).train(False)
+    text = make_batch("expressive", B, 60, 5, seed=901)["in_text_padded"].to(DEV)
+    with torch.no_grad():
+        a0 = T(text).reshape(-1, 32).clone()
+    b0 = torch.randn(B * 34, 32, device=DEV) * 0.5
+    a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    loss = ops_loss.contrastive(a, b, variant)
+    loss.backward()
+    ad, bd = a0.double().requires_grad_(True), b0.double().requires_grad_(True)
+    an, bn = torch.nn.functional.normalize(ad, dim=1), torch.nn.functional.normalize(bd, dim=1)
+    D = (an.unsqueeze(1) - bn.unsqueeze(0)).norm(dim=2)
+    logits = torch.clamp(1.0 / (D + 1e-8), min=1e-8) if variant == "gesture" else 1.0 / D
+    ref = torch.nn.functional.cross_entropy(logits, torch.arange(B * 34, device=DEV))
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    ea = float((a.grad.double() - ad.grad).norm() / ad.grad.norm())
+    eb = float((b.grad.double() - bd.grad).norm() / bd.grad.norm())
+    print(f"contrastive N=4352 {variant}: rel L2 error da {ea:.2e}, db {eb:.2e}")
+    assert ea <= 1e-4 and eb <= 1e-4, (ea, eb)
+
+
+def test_ride_along_rows_match_separate_passes():
+    """ops.ride_along: a generator forward over [G; D; R] rows in one pass (autograd on the G rows only) reproduces three
+    separate passes -- outputs of all three, and every gradient of the differentiated one (hierarchy_net.py:99-149 called
+    three times per step by train_hierarchy_expressive.py:150-213, 252-310, 336-394)."""
+    from ha2g_b200 import ops, rng
+    from ha2g_b200.constants import make_args
+    from ha2g_b200.model.hierarchy_net import Hierarchical_PoseGenerator
+    from ha2g_b200.model.vocab import make_speaker_vocab
+    from ha2g_b200.synthetic import det_fill, make_batch, make_embedding
+    args = make_args("expressive")
+    spk = make_speaker_vocab(5)
+    emb = make_embedding(60, 300, 1).numpy()
+    for B in (3, 40):
+        g = det_fill(Hierarchical_PoseGenerator(args, 30, 60, 300, emb, z_obj=spk), 21).to(DEV)
+        torch.manual_seed(B)
+        text = make_batch("expressive", B, 60, 5, seed=7)["in_text_padded"].to(DEV)
+        pre = [torch.randn(B, 34, 31, device=DEV) * 0.1 for _ in range(3)]
+        aud = torch.randn(B, 34, 32, device=DEV, requires_grad=True)
+        vids = [torch.randint(1, 6, (B,), device=DEV) for _ in range(3)]
+        eps = [torch.randn(B, 16, device=DEV) for _ in range(3)]
+        gout = torch.randn(B, 34, 30, device=DEV)
+        with rng.override(dropout=False):
+            # separate passes
+            sep = []
+            for k in range(3):
+                ctx = torch.enable_grad() if k == 0 else torch.no_grad()
+                with ctx:
+                    sep.append(g(pre[k], text, aud if k == 0 else aud.detach(), vids[k], _eps=eps[k]))
+            (sep[0][0] * gout).sum().backward()
+            ref_grads = {n: p.grad.clone() for n, p in g.named_parameters() if p.grad is not None}
+            ref_daud = aud.grad.clone()
+            g.zero_grad(); aud.grad = None
+            # one ride-along pass
+            pk = lambda ts: ops.ride_pack(ts[0], ts[1:])
+            with ops.ride_along(3):
+                out, z, mu, lv = g(pk(pre), pk([text] * 3), pk([aud, aud, aud]), pk(vids), _eps=pk(eps))
+            assert out.shape == (B, 34, 30) and z.shape == (B, 16)
+            (out * gout).sum().backward()
+        tails_o, tails_z = ops.ride_tails(out, 3), ops.ride_tails(z, 3)
+        assert_close(out, sep[0][0], f"ride head out B={B}", 1e-5)
+        for k in (1, 2):
+            assert_close(tails_o[k - 1], sep[k][0], f"ride tail {k} out B={B}", 1e-5)
+            assert_close(tails_z[k - 1], sep[k][1], f"ride tail {k} z B={B}", 1e-5)
+        assert_close(aud.grad, ref_daud, f"ride d(audio) B={B}", 1e-5)
+        for n, p in g.named_parameters():
+            if n in ref_grads:
+                assert_close(p.grad, ref_grads[n], f"ride grad {n} B={B}", 2e-5)
+            else:
+                assert p.grad is None
