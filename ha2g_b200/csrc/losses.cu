@@ -283,14 +283,16 @@ __device__ __forceinline__ float contrastive_logit(float d, int variant) {
 //         da_i += sum_j c_ij (a_i - b_j)      c_ij = gs * (p_ij - delta_ij) * dl/dD / D,   p_ij = exp(l_ij - lse_i)
 //         (own_is_a == 0): db_j += sum_i c_ij (b_j - a_i)
 template <int MODE>
-__global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __restrict__ own, const float* __restrict__ oth,
+__global__ void __launch_bounds__(CT, 4) contrastive_pair_kernel(const float* __restrict__ own, const float* __restrict__ oth,
                                                               const float* __restrict__ lse, float* __restrict__ part,
                                                               float* __restrict__ diag, float* __restrict__ dgrad,
                                                               const float* __restrict__ gscale, int N, int variant,
                                                               int own_is_a, int cols_per_split, int Noth, int off) {
     // rectangular form (data-parallel global batch): `own` has N rows, `oth` has Noth rows; the loss rows are always the
     // rows of a, whose label is column (row + off) of b.  Square single-GPU case: Noth == N, off == 0.
-    __shared__ float tile[CT][CC + 1];
+    // every lane of a warp reads the SAME tile row (its own row of `own` lives in registers): unpadded rows, 128-bit
+    // broadcast loads -- 8 LDS.128 per pair instead of 32 LDS.32
+    __shared__ __align__(16) float tile[CT][CC];
     __shared__ float tlse[CT];
     const int i = blockIdx.x * CT + threadIdx.x;
     const bool valid = i < N;
@@ -310,10 +312,11 @@ __global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __res
     }
     for (int j0 = j_beg; j0 < j_end; j0 += CT) {
         __syncthreads();
-        for (int e = threadIdx.x; e < CT * CC; e += CT) {
-            int r = e / CC, c = e % CC;
-            int j = j0 + r;
-            tile[r][c] = j < j_end ? oth[(size_t)j * CC + c] : 0.f;
+        for (int e = threadIdx.x; e < CT * CC / 4; e += CT) {   // 16-byte coalesced copies ([N,32] fp32 rows are 128 B)
+            const int r = e / (CC / 4), c4 = e % (CC / 4);
+            const int j = j0 + r;
+            reinterpret_cast<float4*>(&tile[r][0])[c4] =
+                j < j_end ? reinterpret_cast<const float4*>(oth + (size_t)j * CC)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (MODE == 1 && !own_is_a) {
             int j = j0 + threadIdx.x;
@@ -323,9 +326,15 @@ __global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __res
         if (!valid) continue;
         const int cnt = min(CT, j_end - j0);
         for (int r = 0; r < cnt; ++r) {
+            float t[CC];
+#pragma unroll
+            for (int c4 = 0; c4 < CC / 4; ++c4) {
+                const float4 v = reinterpret_cast<const float4*>(&tile[r][0])[c4];
+                t[c4 * 4] = v.x; t[c4 * 4 + 1] = v.y; t[c4 * 4 + 2] = v.z; t[c4 * 4 + 3] = v.w;
+            }
             float d2 = 0.f;
 #pragma unroll
-            for (int c = 0; c < CC; ++c) { float df = me[c] - tile[r][c]; d2 = fmaf(df, df, d2); }
+            for (int c = 0; c < CC; ++c) { float df = me[c] - t[c]; d2 = fmaf(df, df, d2); }
             const float d = sqrtf(d2);
             const float l = contrastive_logit(d, variant);
             const int j = j0 + r;
@@ -343,7 +352,7 @@ __global__ void __launch_bounds__(CT) contrastive_pair_kernel(const float* __res
                 else dld = -1.f / (d * d);
                 float cf = d > 0.f ? gs * p * dld / d : 0.f;
 #pragma unroll
-                for (int c = 0; c < CC; ++c) acc[c] = fmaf(cf, me[c] - tile[r][c], acc[c]);
+                for (int c = 0; c < CC; ++c) acc[c] = fmaf(cf, me[c] - t[c], acc[c]);
             }
         }
     }

@@ -199,9 +199,9 @@ class _ContrastiveFn(torch.autograd.Function):
         variant_id, world, rank = ctx.cfg
         N, Nb = an.shape[0], bn.shape[0]
         dl = _c(dl)
-        dan, dbn = torch.zeros_like(an), torch.zeros_like(bn)
         da, db_all = torch.empty_like(an), torch.empty_like(bn)
-        _call("ha2g_contrastive_bwd_rect", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(dl), _p(dan), _p(dbn), _p(da), _p(db_all),
+        # (the launcher keeps its per-split gradient planes in the scratch arena: no caller-side scratch any more)
+        _call("ha2g_contrastive_bwd_rect", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(dl), None, None, _p(da), _p(db_all),
               N, Nb, rank * N, variant_id, _st())
         if world > 1:
             import torch.distributed as dist
