@@ -123,41 +123,39 @@ __global__ void se_fc_bwd_kernel(const float* __restrict__ ds, const float* __re
     }
 }
 // dw2[c][r] += sum_n dz2[n,c] h[n,r];  db2[c] += sum_n dz2[n,c];  dw1[r][c] += sum_n dz1[n,r] gap[n,c];  db1[r] += sum_n dz1[n,r]
-// one thread per (c, r) pair (+ the bias columns), samples summed in index order (4 independent partial chains, combined
-// in a fixed order: deterministic, and the loads of consecutive samples are in flight together)
+// One CTA per channel c; thread (r, lane) with r in [0, R] (r == R: the bias columns) sums the samples n = lane, lane+8, ...
+// and the 8 lanes are combined in lane order: deterministic, 8 x fewer serial iterations than one thread per (c, r).
 __global__ void se_fc_wgrad_kernel(const float* __restrict__ dz2, const float* __restrict__ dz1, const float* __restrict__ hbuf,
                                    const float* __restrict__ gap, float* __restrict__ dw1, float* __restrict__ db1,
                                    float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int R) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= C * (R + 1)) return;
-    const int c = e / (R + 1), r = e % (R + 1);
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    __shared__ float sa[8][33], sb[8][33];
+    const int c = blockIdx.x, r = threadIdx.x, lane = threadIdx.y;   // blockDim = (R + 1, 8)
+    float a = 0.f, b = 0.f;
     if (r == R) {
-        for (int n0 = 0; n0 < N; n0 += 4) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int n = n0 + k;
-                if (n < N) {
-                    a[k] += dz2[(size_t)n * C + c];
-                    if (c < R) b[k] += dz1[(size_t)n * R + c];
-                }
-            }
+        for (int n = lane; n < N; n += 8) {
+            a += dz2[(size_t)n * C + c];
+            if (c < R) b += dz1[(size_t)n * R + c];
         }
-        db2[c] += (a[0] + a[1]) + (a[2] + a[3]);
-        if (c < R) db1[c] += (b[0] + b[1]) + (b[2] + b[3]);
     } else {
-        for (int n0 = 0; n0 < N; n0 += 4) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int n = n0 + k;
-                if (n < N) {
-                    a[k] = fmaf(dz2[(size_t)n * C + c], hbuf[(size_t)n * R + r], a[k]);
-                    b[k] = fmaf(dz1[(size_t)n * R + r], gap[(size_t)n * C + c], b[k]);
-                }
-            }
+        for (int n = lane; n < N; n += 8) {
+            a = fmaf(dz2[(size_t)n * C + c], hbuf[(size_t)n * R + r], a);
+            b = fmaf(dz1[(size_t)n * R + r], gap[(size_t)n * C + c], b);
         }
-        dw2[c * R + r] += (a[0] + a[1]) + (a[2] + a[3]);
-        dw1[r * C + c] += (b[0] + b[1]) + (b[2] + b[3]);
+    }
+    sa[lane][r] = a;
+    sb[lane][r] = b;
+    __syncthreads();
+    if (lane == 0) {
+        float ta = 0.f, tb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ta += sa[k][r]; tb += sb[k][r]; }
+        if (r == R) {
+            db2[c] += ta;
+            if (c < R) db1[c] += tb;
+        } else {
+            dw2[c * R + r] += ta;
+            dw1[r * C + c] += tb;
+        }
     }
 }
 // acc[i] = scale * (part[0][i] + part[1][i] + ...) in index order
@@ -411,7 +409,7 @@ HA2G_API int ha2g_se_bwd(const float* dout, const float* out, const float* u, co
     if (dz2 == nullptr) return (int)cudaErrorMemoryAllocation;
     float* dz1 = dz2 + (size_t)N * C;
     se_fc_bwd_kernel<<<N, 256, 0, stream>>>(ds, s, h, gap, w1, w2, dz2, dz1, dgap, C, R);
-    se_fc_wgrad_kernel<<<ha2g_div_up(C * (R + 1), 128), 128, 0, stream>>>(dz2, dz1, h, gap, dw1, db1, dw2, db2, N, C, R);
+    se_fc_wgrad_kernel<<<C, dim3(R + 1, 8), 0, stream>>>(dz2, dz1, h, gap, dw1, db1, dw2, db2, N, C, R);
     int64_t total = (int64_t)N * HW * C;
     if (vec)
         se_stream_vec_kernel<1><<<ha2g_ew_grid(total / 4, 256, 4), 256, 0, stream>>>(reinterpret_cast<const float4*>(dres), s, nullptr,

@@ -349,13 +349,13 @@ __global__ void pre_seq_bwd_kernel(const float* __restrict__ dpre, int w,
 #define EW_LAUNCH(kern, n, ...) \
     do { if ((n) > 0) kern<<<ha2g_ew_grid((n)), 256, 0, stream>>>(__VA_ARGS__); HA2G_RETURN_LAST(); } while (0)
 
-// out[c] += sum_r x[r*ld + c]   (out must be initialised by the caller).  Deterministic: up to 16 384 rows one CTA of
-// 32 x 32 threads owns 32 columns over ALL rows (one launch); beyond that row chunks write partial sums into the scratch
-// arena and a second kernel adds them in chunk order.
+// out[c] += sum_r x[r*ld + c]   (out must be initialised by the caller).  Deterministic: up to 1 024 rows one CTA of
+// 32 x 32 threads owns 32 columns over ALL rows (one launch); beyond that row chunks (enough CTAs to cover the SMs) write
+// partial sums into the scratch arena and a second kernel adds them in chunk order.
 HA2G_API int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return 0;
     int gx = ha2g_div_up(cols, 32);
-    if (rows <= 16384) {
+    if (rows <= 1024) {
         col_sum_owner_kernel<<<gx, dim3(32, 32), 0, stream>>>(x, rows, cols, ld, out);
         HA2G_RETURN_LAST();
     }

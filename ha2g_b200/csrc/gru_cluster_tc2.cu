@@ -170,9 +170,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     float* hown = reinterpret_cast<float*>(smem + L.off_hown);   // [HSP][NB]
     float* outst = reinterpret_cast<float*>(smem + L.off_out);   // [5][NB][orow]
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    uint64_t* bar_full = bar_mma + 1;                   // [2]: h buffer b complete (8 x slice_bytes landed)
-    uint64_t* bar_w = bar_mma + 3;                      // one-time: the W_hh rows have landed in shared memory
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
+    uint64_t* bar_full = bar_mma + 1;                   // [2][4]: h buffer b, slices of rank pair p complete (2 x slice_bytes)
+    uint64_t* bar_w = bar_mma + 9;                      // one-time: the W_hh rows have landed in shared memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 10);
     const float* wrows = reinterpret_cast<const float*>(smem + L.off_w);   // [3*HSP][H]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = ha2g_warp_id();   // provably warp-uniform
@@ -186,14 +186,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     float* __restrict__ g_gates = p.gates;
     long long* g_dbg = p.dbg;
     const int M_gates = p.M_gates;
-    const uint32_t tx_bytes = (uint32_t)(CL * L.slice_bytes);
+    const uint32_t tx_bytes = (uint32_t)(2 * L.slice_bytes);   // per rank-pair barrier
 
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
     if (dbg_on && tid == 0) p.dbg[p.T * 8 + 0] = clock64();
     if (tid == 0) {
         mbi(bar_mma, 1);
-        mbi(bar_full + 0, 1);
-        mbi(bar_full + 1, 1);
+        for (int i = 0; i < 8; ++i) mbi(bar_full + i, 1);
         mbi(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -306,70 +305,83 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
         for (int e = tid; e < HSP * NB; e += TNT) hown[e] = 0.f;
         asm volatile("fence.proxy.async;" ::: "memory");
         if (tid == 0) {   // h_0 lands in buffer 1 (consumed by step 1), h_1 in buffer 0 (consumed by step 2)
-            if (T >= 2) mb_expect_tx(bar_full + 1, tx_bytes);
-            if (T >= 3) mb_expect_tx(bar_full + 0, tx_bytes);
+            for (int pr = 0; pr < 4; ++pr) {
+                if (T >= 2) mb_expect_tx(bar_full + 4 + pr, tx_bytes);
+                if (T >= 3) mb_expect_tx(bar_full + pr, tx_bytes);
+            }
         }
         cluster.sync();
         if (dbg_on && tid == 0) g_dbg[p.T * 8 + 3] = clock64();
+        // x-side pre-activations of this thread's 8 units for one step (independent of the recurrence).  They are loaded
+        // one step AHEAD, before the y / gate copy-out of the current step fills the load/store queue, so that they are
+        // in registers long before the gate math needs them.
+        float gir[8], giz[8], gin[8];
+        auto load_gi = [&](int s_next) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gir[i] = giz[i] = gin[i] = 0.f;
+            const int b = m0 + bb;
+            const int jbase = j0 + cc * 8;
+            if (!(has_item && b < M) || s_next >= T) return;
+            const int tn = dir == 0 ? s_next : T - 1 - s_next;
+            const float* g = g_gi + (((size_t)b * T + tn) * 2 + dir) * 3 * H;
+            if (jbase + 7 < H) {   // whole 8-unit chunk valid -> 128-bit accesses (rows are 16-byte aligned)
+                const float4 r0 = *reinterpret_cast<const float4*>(g + jbase), r1 = *reinterpret_cast<const float4*>(g + jbase + 4);
+                const float4 z0 = *reinterpret_cast<const float4*>(g + H + jbase), z1 = *reinterpret_cast<const float4*>(g + H + jbase + 4);
+                const float4 n0 = *reinterpret_cast<const float4*>(g + 2 * H + jbase), n1 = *reinterpret_cast<const float4*>(g + 2 * H + jbase + 4);
+                gir[0] = r0.x; gir[1] = r0.y; gir[2] = r0.z; gir[3] = r0.w; gir[4] = r1.x; gir[5] = r1.y; gir[6] = r1.z; gir[7] = r1.w;
+                giz[0] = z0.x; giz[1] = z0.y; giz[2] = z0.z; giz[3] = z0.w; giz[4] = z1.x; giz[5] = z1.y; giz[6] = z1.z; giz[7] = z1.w;
+                gin[0] = n0.x; gin[1] = n0.y; gin[2] = n0.z; gin[3] = n0.w; gin[4] = n1.x; gin[5] = n1.y; gin[6] = n1.z; gin[7] = n1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = jbase + i;
+                    if (j < H) { gir[i] = g[j]; giz[i] = g[H + j]; gin[i] = g[2 * H + j]; }
+                }
+            }
+        };
+        if (is_epi) load_gi(0);
         for (int s = 0; s < T; ++s, ++it) {
             const int t = dir == 0 ? s : T - 1 - s;
             const int cur = s & 1;
             // ---- tensor core: D[128 x 16] = W_slice * h_{t-1}^T ------------------------------------------------
             if (warp == 0) {   // whole warp, converged; one elected lane issues
                 if (dbg_on && lane == 0) g_dbg[s * 8 + 7] = clock64();
-                if (s > 0) {
-                    mbw_cluster(bar_full + cur, cur ? full_ph1 : full_ph0);
-                    if (cur) full_ph1 ^= 1; else full_ph0 ^= 1;
-                }
-                if (dbg_on && lane == 0) g_dbg[s * 8 + 0] = clock64();
-                // st.async data (generic proxy of the peers) -> visible to the tensor core's async proxy
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (ha2g_elect_one()) {
-                    if (s > 0 && s + 2 <= T - 1) mb_expect_tx(bar_full + cur, tx_bytes);   // h_{s+1} will land here
-                    uint32_t ah = tmem_ahi, al = tmem_alo;
-                    uint64_t dbh = cur ? dbh1 : dbh0, dbl = cur ? dbl1 : dbl0;
-                    mma16_ts(tmem_d, ah, dbh, idesc, 0u);
-                    mma16_ts(tmem_d, ah, dbl, idesc, 1u);
-                    mma16_ts(tmem_d, al, dbh, idesc, 1u);
-#pragma unroll 4
-                    for (int ks = 1; ks < KC / 2; ++ks) {
-                        ah += 8; al += 8; dbh += b_step; dbl += b_step;
-                        mma16_ts(tmem_d, ah, dbh, idesc, 1u);
-                        mma16_ts(tmem_d, ah, dbl, idesc, 1u);
-                        mma16_ts(tmem_d, al, dbh, idesc, 1u);
+                // The K range is consumed rank pair by rank pair (pair p = K chunks [p*2*CPC, (p+1)*2*CPC)): the MMAs over
+                // a pair's slices are issued as soon as THAT pair's st.async traffic has landed, so the tensor work runs
+                // under the arrival of the remaining slices instead of after the last one.
+                const int kpp = CPC;            // K = 16 steps per rank pair (2*CPC chunks of 8)
+                const uint64_t dbh_base = cur ? dbh1 : dbh0, dbl_base = cur ? dbl1 : dbl0;
+                for (int pr = 0; pr < 4; ++pr) {
+                    if (s > 0) mbw_cluster(bar_full + cur * 4 + pr, cur ? full_ph1 : full_ph0);
+                    if (dbg_on && lane == 0 && pr == 0) g_dbg[s * 8 + 0] = clock64();
+                    // st.async data (generic proxy of the peers) -> visible to the tensor core's async proxy
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (ha2g_elect_one()) {
+                        if (s > 0 && s + 2 <= T - 1) mb_expect_tx(bar_full + cur * 4 + pr, tx_bytes);   // h_{s+1} will land here
+                        for (int ks = 0; ks < kpp; ++ks) {
+                            // operands from warp-uniform values only (uniform-datapath issue, see common.cuh)
+                            const uint32_t kk = (uint32_t)(pr * kpp + ks);
+                            const uint32_t ah = tmem_ahi + 8u * kk, al = tmem_alo + 8u * kk;
+                            const uint64_t dbh = dbh_base + b_step * kk, dbl = dbl_base + b_step * kk;
+                            mma16_ts(tmem_d, ah, dbh, idesc, kk ? 1u : 0u);
+                            mma16_ts(tmem_d, ah, dbl, idesc, 1u);
+                            mma16_ts(tmem_d, al, dbh, idesc, 1u);
+                        }
+                        if (pr == 3)
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar_mma)) : "memory");
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar_mma)) : "memory");
+                    __syncwarp();
                 }
+                if (s > 0) { if (cur) full_ph1 ^= 1; else full_ph0 ^= 1; }
                 __syncwarp();
                 if (dbg_on && lane == 0) g_dbg[s * 8 + 1] = clock64();
             }
             if (is_epi) {
-                // x-side pre-activations for this thread's 8 units (independent of the recurrence: issued before the wait)
-                float gir[8], giz[8], gin[8];
+                // (the x-side pre-activations gir/giz/gin of this step were prefetched before the previous step's copy-out)
                 const int b = m0 + bb;
                 const int jbase = j0 + cc * 8;
                 const bool live = has_item && b < M;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) gir[i] = giz[i] = gin[i] = 0.f;
-                const bool full8 = jbase + 7 < H;   // whole 8-unit chunk valid -> 128-bit accesses (rows are 16-byte aligned)
-                if (live) {
-                    const float* g = g_gi + (((size_t)b * T + t) * 2 + dir) * 3 * H;
-                    if (full8) {
-                        const float4 r0 = *reinterpret_cast<const float4*>(g + jbase), r1 = *reinterpret_cast<const float4*>(g + jbase + 4);
-                        const float4 z0 = *reinterpret_cast<const float4*>(g + H + jbase), z1 = *reinterpret_cast<const float4*>(g + H + jbase + 4);
-                        const float4 n0 = *reinterpret_cast<const float4*>(g + 2 * H + jbase), n1 = *reinterpret_cast<const float4*>(g + 2 * H + jbase + 4);
-                        gir[0] = r0.x; gir[1] = r0.y; gir[2] = r0.z; gir[3] = r0.w; gir[4] = r1.x; gir[5] = r1.y; gir[6] = r1.z; gir[7] = r1.w;
-                        giz[0] = z0.x; giz[1] = z0.y; giz[2] = z0.z; giz[3] = z0.w; giz[4] = z1.x; giz[5] = z1.y; giz[6] = z1.z; giz[7] = z1.w;
-                        gin[0] = n0.x; gin[1] = n0.y; gin[2] = n0.z; gin[3] = n0.w; gin[4] = n1.x; gin[5] = n1.y; gin[6] = n1.z; gin[7] = n1.w;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int j = jbase + i;
-                            if (j < H) { gir[i] = g[j]; giz[i] = g[H + j]; gin[i] = g[2 * H + j]; }
-                        }
-                    }
-                }
                 mbw(bar_mma, it & 1);
                 if (dbg_on && tid == 32) g_dbg[s * 8 + 2] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -432,7 +444,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                         const uint32_t dst_hi = su32(hbuf) + (uint32_t)((size_t)(cur ^ 1) * L.b_bytes +
                                                                        ((size_t)((rank * CPC + cc) * 2 + 0) * NB + bb) * 16);
                         const uint32_t dst_lo = dst_hi + NB * 16;
-                        const uint32_t bar = su32(bar_full + (cur ^ 1));
+                        const uint32_t bar = su32(bar_full + (cur ^ 1) * 4 + (rank >> 1));
 #pragma unroll
                         for (uint32_t d = 0; d < CL; ++d) {
                             const uint32_t rbar = mapa(bar, d);
@@ -442,6 +454,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                     }
                     if (dbg_on && tid == 32) g_dbg[s * 8 + 5] = clock64();
                 }
+                load_gi(s + 1);   // next step's x-side pre-activations: issued before the stores below
                 // ---- y and the saved gates: off the critical path (the next step's MMA is already being fed), staged
                 // through shared memory so that the global stores are 160-byte runs instead of 32 scattered sectors per
                 // instruction (the scattered version kept the LSU busy for ~1 000 cycles per step)

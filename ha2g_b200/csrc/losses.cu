@@ -450,7 +450,7 @@ HA2G_API int ha2g_contrastive_fwd_rect(const float* a, const float* b, float* an
                                        float* lse, float* part, float* diag, int Na, int Nb, int off, int variant,
                                        float* loss, cudaStream_t stream) {
     const int rows_ctas = ha2g_div_up(Na, CT);
-    int S = (148 * 2 + rows_ctas - 1) / rows_ctas;
+    int S = (148 * 4 + rows_ctas - 1) / rows_ctas;      // 4 resident CTAs per SM (launch bounds of the pair kernel)
     const int max_s = ha2g_div_up(Nb, CT);
     if (S > max_s) S = max_s;
     if (S < 1) S = 1;
@@ -469,7 +469,7 @@ HA2G_API int ha2g_contrastive_bwd_rect(const float* an, const float* bn, const f
                                        int off, int variant, cudaStream_t stream) {
     auto splits = [](int rows, int oth) {
         const int rc = (rows + CT - 1) / CT;
-        int S = (148 * 2 + rc - 1) / rc;
+        int S = (148 * 4 + rc - 1) / rc;
         const int mx = (oth + CT - 1) / CT;
         if (S > mx) S = mx;
         if (S < 1) S = 1;

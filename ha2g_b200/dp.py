@@ -2,8 +2,9 @@
 
 The reference wraps every module in single-process ``nn.DataParallel`` (scripts/train_expressive.py:184-197):
 scatter the batch, replicate weights, gather outputs, reduce-add gradients onto GPU 0, step there.  Here each
-rank owns a full replica and its own B_local clips; after each backward the gradients of the optimizer about to step
-are averaged across ranks (bucketed flat all-reduce), so every replica applies the identical Adam update.
+rank owns a full replica and its own B_local clips; the gradients of each optimizer are averaged across ranks in place
+(one coalesced NCCL all-reduce, launched from autograd hooks while the rest of the backward pass still runs), so every
+replica applies the identical Adam update.
 BatchNorm statistics stay per-rank, exactly like DataParallel's per-replica statistics.
 
 The contrastive loss runs over the GLOBAL batch like the reference's DataParallel step: each rank
@@ -21,7 +22,6 @@ import torch
 
 _state = {"world": 1, "enabled": False, "rank": 0,
           "global_contrastive": os.environ.get("HA2G_DP_LOCAL_CONTRASTIVE", "0") != "1"}
-BUCKET_BYTES = 64 << 20
 
 
 def enable(world_size: int, modules: Optional[List[torch.nn.Module]] = None, broadcast: bool = True):
@@ -38,6 +38,9 @@ def enable(world_size: int, modules: Optional[List[torch.nn.Module]] = None, bro
 
 def disable():
     _state["world"], _state["enabled"], _state["rank"] = 1, False, 0
+    end_backward()
+    _known.clear()
+    _inflight.clear()
 
 
 def rank() -> int:
@@ -52,35 +55,86 @@ def world_size() -> int:
     return _state["world"]
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# gradient averaging: in place, coalesced, overlapped with the backward pass
+# ---------------------------------------------------------------------------------------------------------------
+# One coalesced NCCL all-reduce (ncclAvg) per optimizer over the gradient tensors themselves: no flatten copy, no
+# divide pass, no copy-back.  During the generator step's backward the all-reduce of an optimizer is LAUNCHED from
+# autograd hooks the moment the last gradient of that optimizer has been accumulated (generator k's gradients are final
+# when its BPTT ends, while generators k-1..1 and the encoders are still being differentiated): it runs on NCCL's stream
+# concurrently with the rest of the backward pass, and ``allreduce_grads`` -- called right before the optimizer's Adam
+# launch -- only waits for it.  Under CUDA-graph capture the same fork / join is recorded into the step's graph.
+_known = {}        # id(optimizer) -> parameters that received a gradient in the previous step (what the hooks count)
+_inflight = {}     # id(optimizer) -> pending work of an all-reduce launched from the hooks
+_handles: List = []
+
+
+def _avg_supported() -> bool:
+    import torch.distributed as dist
+    return dist.get_backend() == "nccl"
+
+
 @torch.no_grad()
-def allreduce_grads(optimizer: torch.optim.Optimizer):
-    """Average the gradients of ``optimizer``'s parameters over all ranks (flat buckets of <= 64 MiB)."""
+def _launch(grads, async_op: bool):
+    """Average `grads` in place over all ranks with one coalesced collective.  -> work handle (async) or None."""
+    import torch.distributed as dist
+    if not grads:
+        return None
+    avg = _avg_supported()
+    op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+    dev = grads[0].device if grads[0].is_cuda else None
+    with dist._coalescing_manager(device=dev, async_ops=async_op) as cm:
+        for g in grads:
+            dist.all_reduce(g, op=op)
+    if not avg:      # gloo (CPU tests): no AVG reduction
+        if async_op:
+            cm.wait()
+        w = float(_state["world"])
+        for g in grads:
+            g.div_(w)
+        return None
+    return cm if async_op else None
+
+
+def begin_backward(optimizers):
+    """Arm the overlap for one backward pass: install per-parameter hooks that launch an optimizer's all-reduce as soon
+    as all of its gradients exist.  No-op on one GPU and before an optimizer's gradient set is known (first step)."""
     if not _state["enabled"]:
         return
-    import torch.distributed as dist
-    grads = [p.grad for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
-    if not grads:
+    for opt in optimizers:
+        params = _known.get(id(opt))
+        if not params:
+            continue
+        st = {"left": len(params), "opt": opt, "params": params}
+
+        def hook(_p, st=st):
+            st["left"] -= 1
+            if st["left"] == 0:
+                _inflight[id(st["opt"])] = (_launch([q.grad for q in st["params"]], True), st["params"])
+        for p in params:
+            _handles.append(p.register_post_accumulate_grad_hook(hook))
+
+
+def end_backward():
+    for h in _handles:
+        h.remove()
+    _handles.clear()
+
+
+@torch.no_grad()
+def allreduce_grads(optimizer: torch.optim.Optimizer):
+    """Make ``optimizer``'s gradients the average over all ranks: wait for the all-reduce launched during backward, or run
+    it now (first step, discriminator step, parameters whose gradient set changed)."""
+    if not _state["enabled"]:
         return
-    w = float(_state["world"])
-    bucket, size = [], 0
-
-    def flush():
-        nonlocal bucket, size
-        if not bucket:
-            return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat)
-        flat.div_(w)
-        off = 0
-        for g in bucket:
-            n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
-            off += n
-        bucket, size = [], 0
-
-    for g in grads:
-        bucket.append(g)
-        size += g.numel() * 4
-        if size >= BUCKET_BYTES:
-            flush()
-    flush()
+    params = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
+    pending = _inflight.pop(id(optimizer), None)
+    if pending is not None:
+        work, launched = pending
+        if work is not None:
+            work.wait()
+        if len(launched) != len(params) or any(a is not b for a, b in zip(launched, params)):
+            raise RuntimeError("the set of parameters receiving gradients changed while an all-reduce was in flight")
+    else:
+        _launch([p.grad for p in params], False)
+    _known[id(optimizer)] = params

@@ -188,10 +188,18 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
         mdv = [float(v[0]) if isinstance(v, (list, tuple)) else float(v) for v in args.mean_dir_vec]
         add("phy", ops_loss.physical(out_dir_vec, variant, mdv), args.loss_physical_weight)
 
-    torch.autograd.backward(roots, root_w)
+    g_opts = list(gen_optimizers) + [audio_optimizer, text_optimizer]
+    dp.begin_backward(g_opts)     # data parallel: all-reduces are launched from gradient hooks DURING the backward pass
+    try:
+        torch.autograd.backward(roots, root_w)
+    finally:
+        dp.end_backward()
 
-    for opt in list(gen_optimizers) + [audio_optimizer, text_optimizer]:
-        dp.allreduce_grads(opt)   # no-op on one GPU
+    for opt in reversed(g_opts[:len(gen_optimizers)]):   # g_L's gradients (and its all-reduce) finish first
+        dp.allreduce_grads(opt)   # no-op on one GPU; otherwise waits for the overlapped all-reduce
+        adam(opt)
+    for opt in (audio_optimizer, text_optimizer):
+        dp.allreduce_grads(opt)
         adam(opt)
 
     # ------------------------------------------------------------------ one packed device->host read

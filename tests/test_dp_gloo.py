@@ -26,7 +26,6 @@ def _worker(rank, world, port, q):
     x = torch.randn(4, 7, generator=g)
     model(x).pow(2).sum().backward()
     local = [p.grad.clone() for p in model.parameters()]
-    dp.BUCKET_BYTES = 64  # force several buckets
     dp.allreduce_grads(opt)
     opt.step()
     gathered = [torch.zeros_like(torch.cat([l.reshape(-1) for l in local])) for _ in range(world)]
@@ -36,7 +35,20 @@ def _worker(rank, world, port, q):
     params = torch.cat([p.data.reshape(-1) for p in model.parameters()])
     allp = [torch.zeros_like(params) for _ in range(world)]
     dist.all_gather(allp, params)
-    q.put((rank, float((got - mean).abs().max()), float((allp[0] - allp[1]).abs().max())))
+    # second step: the gradient set is known now, so the all-reduce is launched from the autograd hooks during backward
+    opt.zero_grad(set_to_none=True)
+    x2 = torch.randn(4, 7, generator=g)
+    dp.begin_backward([opt])
+    model(x2).pow(2).sum().backward()
+    dp.end_backward()
+    hooked = id(opt) in dp._inflight
+    local2 = torch.cat([p.grad.reshape(-1) for p in model.parameters()])   # gloo path: already averaged in place
+    dp.allreduce_grads(opt)
+    got2 = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    both = [torch.zeros_like(got2) for _ in range(world)]
+    dist.all_gather(both, got2)
+    q.put((rank, float((got - mean).abs().max()), float((allp[0] - allp[1]).abs().max()), hooked,
+           float((both[0] - both[1]).abs().max()), float((local2 - got2).abs().max())))
     dist.destroy_process_group()
 
 
@@ -51,6 +63,8 @@ def test_allreduce_grads_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, gerr, perr in res:
+    for rank, gerr, perr, hooked, g2_rank_diff, g2_changed in res:
         assert gerr < 1e-6, (rank, gerr)
         assert perr == 0.0, (rank, perr)
+        assert hooked, "the second backward did not launch the all-reduce from the gradient hooks"
+        assert g2_rank_diff == 0.0 and g2_changed == 0.0, (rank, g2_rank_diff, g2_changed)
