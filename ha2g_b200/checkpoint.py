@@ -98,3 +98,29 @@ def load_checkpoint_hierarchy(path: str, _device="cuda:0"):
     audio_encoder = audio_encoder.to(_device).train(False)
     loss_fn = torch.nn.L1Loss()   # train_expressive.py:127 (returned for signature compatibility; unused by the step)
     return (args, *gens, audio_encoder, loss_fn, lang_model, speaker_model, pose_dim)
+
+
+def resume_training(path: str, gens: Sequence, discriminator, audio_encoder, text_encoder,
+                    optimizers: Optional[dict] = None) -> int:
+    """Restore a training run in place from a checkpoint written by ``save_checkpoint_hierarchy`` (or by the reference's
+    ``train_epochs``, which stores no optimizer state: the moments then restart from zero, as they would there):
+    module weights and buffers of every generator, the discriminator and both encoders, and -- when the file carries
+    ``optim_dicts`` and ``optimizers`` names the same keys -- the Adam moments and step counts.  Returns the stored epoch.
+    The captured CUDA graph of the step (if any) notices the re-allocated moment tensors and re-captures itself
+    (graph_step._still_valid)."""
+    ck = read_checkpoint(path)
+    L = sum(1 for k in ck if k.startswith("gen_dict_"))
+    if L != len(gens):
+        raise ValueError(f"checkpoint holds {L} generators, the run has {len(gens)}")
+    for k, g in enumerate(gens, start=1):
+        g.load_state_dict(ck[f"gen_dict_{k}"])
+    if discriminator is not None and ck.get("dis_dict") is not None:
+        discriminator.load_state_dict(ck["dis_dict"])
+    audio_encoder.load_state_dict(ck["audio_dict"])
+    if text_encoder is not None and ck.get("text_dict") is not None:
+        text_encoder.load_state_dict(ck["text_dict"])
+    if optimizers and ck.get("optim_dicts"):
+        for name, opt in optimizers.items():
+            if name in ck["optim_dicts"]:
+                opt.load_state_dict(ck["optim_dicts"][name])
+    return int(ck["epoch"])

@@ -618,3 +618,34 @@ HA2G_API int ha2g_dropout(const float* x, float* y, int64_t n, float p, const ui
                                                                           reinterpret_cast<const unsigned long long*>(state), call_id);
     HA2G_RETURN_LAST();
 }
+
+namespace {
+// one thread per clip: the reference's sequential loop (later words overwrite earlier ones on the same frame)
+__global__ void place_words_kernel(const int64_t* __restrict__ word_id, const double* __restrict__ word_start,
+                                   const int* __restrict__ word_off, const double* __restrict__ clip_start,
+                                   const double* __restrict__ clip_end, int B, int n_frames, int64_t* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int64_t* row = out + (size_t)b * n_frames;
+    for (int f = 0; f < n_frames; ++f) row[f] = 0;   // 0 = PAD
+    const double st = clip_start[b];
+    const double frame_duration = (clip_end[b] - st) / (double)n_frames;
+    for (int w = word_off[b]; w < word_off[b + 1]; ++w) {
+        int idx = (int)floor((word_start[w] - st) / frame_duration);
+        if (idx < 0) idx = 0;
+        if (idx < n_frames) row[idx] = word_id[w];
+    }
+}
+}  // namespace
+
+// extended_word_seq of a whole batch on the device (SpeechMotionDataset.extend_word_seq,
+// scripts/data_loader/lmdb_data_loader_expressive.py:116-141, timing-preserving branch): clip b owns the words
+// [word_off[b], word_off[b+1]); word w lands on frame max(0, floor((word_start[w] - clip_start[b]) / frame_duration)) when that
+// is < n_frames, with frame_duration = (clip_end[b] - clip_start[b]) / n_frames evaluated in float64 like the reference's
+// Python arithmetic -- bit-exact index contract.  out [B, n_frames] int64.
+HA2G_API int ha2g_place_words(const int64_t* word_id, const double* word_start, const int* word_off, const double* clip_start,
+                              const double* clip_end, int B, int n_frames, int64_t* out, cudaStream_t stream) {
+    if (B <= 0) return 0;
+    place_words_kernel<<<ha2g_div_up(B, 128), 128, 0, stream>>>(word_id, word_start, word_off, clip_start, clip_end, B, n_frames, out);
+    HA2G_RETURN_LAST();
+}

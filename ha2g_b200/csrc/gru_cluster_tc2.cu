@@ -170,9 +170,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     float* hown = reinterpret_cast<float*>(smem + L.off_hown);   // [HSP][NB]
     float* outst = reinterpret_cast<float*>(smem + L.off_out);   // [5][NB][orow]
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    uint64_t* bar_full = bar_mma + 1;                   // [2][4]: h buffer b, slices of rank pair p complete (2 x slice_bytes)
-    uint64_t* bar_w = bar_mma + 9;                      // one-time: the W_hh rows have landed in shared memory
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 10);
+    uint64_t* bar_full = bar_mma + 1;                   // [2]: h buffer b complete (8 x slice_bytes landed)
+    uint64_t* bar_w = bar_mma + 3;                      // one-time: the W_hh rows have landed in shared memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
     const float* wrows = reinterpret_cast<const float*>(smem + L.off_w);   // [3*HSP][H]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = ha2g_warp_id();   // provably warp-uniform
@@ -186,13 +186,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     float* __restrict__ g_gates = p.gates;
     long long* g_dbg = p.dbg;
     const int M_gates = p.M_gates;
-    const uint32_t tx_bytes = (uint32_t)(2 * L.slice_bytes);   // per rank-pair barrier
+    const uint32_t tx_bytes = (uint32_t)(CL * L.slice_bytes);
 
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
     if (dbg_on && tid == 0) p.dbg[p.T * 8 + 0] = clock64();
     if (tid == 0) {
         mbi(bar_mma, 1);
-        for (int i = 0; i < 8; ++i) mbi(bar_full + i, 1);
+        mbi(bar_full + 0, 1);
+        mbi(bar_full + 1, 1);
         mbi(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -305,10 +306,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
         for (int e = tid; e < HSP * NB; e += TNT) hown[e] = 0.f;
         asm volatile("fence.proxy.async;" ::: "memory");
         if (tid == 0) {   // h_0 lands in buffer 1 (consumed by step 1), h_1 in buffer 0 (consumed by step 2)
-            for (int pr = 0; pr < 4; ++pr) {
-                if (T >= 2) mb_expect_tx(bar_full + 4 + pr, tx_bytes);
-                if (T >= 3) mb_expect_tx(bar_full + pr, tx_bytes);
-            }
+            if (T >= 2) mb_expect_tx(bar_full + 1, tx_bytes);
+            if (T >= 3) mb_expect_tx(bar_full + 0, tx_bytes);
         }
         cluster.sync();
         if (dbg_on && tid == 0) g_dbg[p.T * 8 + 3] = clock64();
@@ -346,34 +345,32 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
             // ---- tensor core: D[128 x 16] = W_slice * h_{t-1}^T ------------------------------------------------
             if (warp == 0) {   // whole warp, converged; one elected lane issues
                 if (dbg_on && lane == 0) g_dbg[s * 8 + 7] = clock64();
-                // The K range is consumed rank pair by rank pair (pair p = K chunks [p*2*CPC, (p+1)*2*CPC)): the MMAs over
-                // a pair's slices are issued as soon as THAT pair's st.async traffic has landed, so the tensor work runs
-                // under the arrival of the remaining slices instead of after the last one.
-                const int kpp = CPC;            // K = 16 steps per rank pair (2*CPC chunks of 8)
-                const uint64_t dbh_base = cur ? dbh1 : dbh0, dbl_base = cur ? dbl1 : dbl0;
-                for (int pr = 0; pr < 4; ++pr) {
-                    if (s > 0) mbw_cluster(bar_full + cur * 4 + pr, cur ? full_ph1 : full_ph0);
-                    if (dbg_on && lane == 0 && pr == 0) g_dbg[s * 8 + 0] = clock64();
-                    // st.async data (generic proxy of the peers) -> visible to the tensor core's async proxy
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (ha2g_elect_one()) {
-                        if (s > 0 && s + 2 <= T - 1) mb_expect_tx(bar_full + cur * 4 + pr, tx_bytes);   // h_{s+1} will land here
-                        for (int ks = 0; ks < kpp; ++ks) {
-                            // operands from warp-uniform values only (uniform-datapath issue, see common.cuh)
-                            const uint32_t kk = (uint32_t)(pr * kpp + ks);
-                            const uint32_t ah = tmem_ahi + 8u * kk, al = tmem_alo + 8u * kk;
-                            const uint64_t dbh = dbh_base + b_step * kk, dbl = dbl_base + b_step * kk;
-                            mma16_ts(tmem_d, ah, dbh, idesc, kk ? 1u : 0u);
-                            mma16_ts(tmem_d, ah, dbl, idesc, 1u);
-                            mma16_ts(tmem_d, al, dbh, idesc, 1u);
-                        }
-                        if (pr == 3)
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar_mma)) : "memory");
-                    }
-                    __syncwarp();
+                // (measured: splitting the wait into per-rank-pair barriers so that the MMAs start under the arrival of the
+                // remaining slices LOST 4-14 % -- the slices land together, and every extra acquire wait costs a CCTL.IVALL)
+                if (s > 0) {
+                    mbw_cluster(bar_full + cur, cur ? full_ph1 : full_ph0);
+                    if (cur) full_ph1 ^= 1; else full_ph0 ^= 1;
                 }
-                if (s > 0) { if (cur) full_ph1 ^= 1; else full_ph0 ^= 1; }
+                if (dbg_on && lane == 0) g_dbg[s * 8 + 0] = clock64();
+                // st.async data (generic proxy of the peers) -> visible to the tensor core's async proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (ha2g_elect_one()) {
+                    if (s > 0 && s + 2 <= T - 1) mb_expect_tx(bar_full + cur, tx_bytes);   // h_{s+1} will land here
+                    uint32_t ah = tmem_ahi, al = tmem_alo;
+                    uint64_t dbh = cur ? dbh1 : dbh0, dbl = cur ? dbl1 : dbl0;
+                    mma16_ts(tmem_d, ah, dbh, idesc, 0u);
+                    mma16_ts(tmem_d, ah, dbl, idesc, 1u);
+                    mma16_ts(tmem_d, al, dbh, idesc, 1u);
+#pragma unroll 4
+                    for (int ks = 1; ks < KC / 2; ++ks) {
+                        ah += 8; al += 8; dbh += b_step; dbl += b_step;
+                        mma16_ts(tmem_d, ah, dbh, idesc, 1u);
+                        mma16_ts(tmem_d, ah, dbl, idesc, 1u);
+                        mma16_ts(tmem_d, al, dbh, idesc, 1u);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar_mma)) : "memory");
+                }
                 __syncwarp();
                 if (dbg_on && lane == 0) g_dbg[s * 8 + 1] = clock64();
             }
@@ -444,7 +441,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                         const uint32_t dst_hi = su32(hbuf) + (uint32_t)((size_t)(cur ^ 1) * L.b_bytes +
                                                                        ((size_t)((rank * CPC + cc) * 2 + 0) * NB + bb) * 16);
                         const uint32_t dst_lo = dst_hi + NB * 16;
-                        const uint32_t bar = su32(bar_full + (cur ^ 1) * 4 + (rank >> 1));
+                        const uint32_t bar = su32(bar_full + (cur ^ 1));
 #pragma unroll
                         for (uint32_t d = 0; d < CL; ++d) {
                             const uint32_t rbar = mapa(bar, d);

@@ -505,3 +505,47 @@ HA2G_API int ha2g_contrastive_bwd(const float* an, const float* bn, const float*
                                   cudaStream_t stream) {
     return ha2g_contrastive_bwd_rect(an, bn, na, nb, lse, gscale, dan, dbn, da, db, N, N, 0, variant, stream);
 }
+
+namespace {
+// FGD evaluator side metrics (scripts/model/embedding_space_evaluator.py:75-99), one CTA per sample b:
+//   rec[b] = mean_{t,d} |recon - pose| + mean_{t<T-1,d} |(recon[t+1]-recon[t]) - (pose[t+1]-pose[t])|
+//   cs[b]  = sum_{t,j} (1 - cos(recon[t,3j:3j+3], pose[t,3j:3j+3]))      (torch.cosine_similarity: eps 1e-8 on each norm)
+__global__ void recon_metrics_kernel(const float* __restrict__ recon, const float* __restrict__ pose, int T, int D,
+                                     float* __restrict__ rec, float* __restrict__ cs) {
+    __shared__ float sh[33];
+    const int b = blockIdx.x;
+    const float* r = recon + (size_t)b * T * D;
+    const float* p = pose + (size_t)b * T * D;
+    float a = 0.f, d = 0.f, c = 0.f;
+    for (int e = threadIdx.x; e < T * D; e += blockDim.x) {
+        a += fabsf(r[e] - p[e]);
+        if (e < (T - 1) * D) d += fabsf((r[e + D] - r[e]) - (p[e + D] - p[e]));
+    }
+    const int J = D / 3;
+    for (int e = threadIdx.x; e < T * J; e += blockDim.x) {
+        const float* rv = r + (size_t)e * 3;
+        const float* pv = p + (size_t)e * 3;
+        const float dot = rv[0] * pv[0] + rv[1] * pv[1] + rv[2] * pv[2];
+        const float nr = fmaxf(sqrtf(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]), 1e-8f);
+        const float np = fmaxf(sqrtf(pv[0] * pv[0] + pv[1] * pv[1] + pv[2] * pv[2]), 1e-8f);
+        c += 1.f - dot / (nr * np);
+    }
+    a = block_sum(a, sh);
+    d = block_sum(d, sh);
+    c = block_sum(c, sh);
+    if (threadIdx.x == 0) {
+        rec[b] = a / (float)(T * D) + d / (float)((T - 1) * D);
+        cs[b] = c;
+    }
+}
+}  // namespace
+
+// Per-sample reconstruction / cosine errors of the FGD auto-encoder's output against its input: recon, pose [B,T,D]
+// (D = 3 * joints) -> rec [B], cs [B]   (EmbeddingSpaceEvaluator.push_samples, embedding_space_evaluator.py:75-99)
+HA2G_API int ha2g_recon_metrics(const float* recon, const float* pose, int B, int T, int D, float* rec, float* cs,
+                                cudaStream_t stream) {
+    if (B <= 0) return 0;
+    if (D % 3 != 0 || T < 2) return (int)cudaErrorInvalidValue;
+    recon_metrics_kernel<<<B, 256, 0, stream>>>(recon, pose, T, D, rec, cs);
+    HA2G_RETURN_LAST();
+}

@@ -14,7 +14,7 @@ import torch
 from ._lib import lib
 from . import rng as _rng
 
-ACT_NONE, ACT_RELU, ACT_LRELU, ACT_ELU, ACT_SIGMOID, ACT_TANH = range(6)
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_ELU, ACT_SIGMOID, ACT_TANH, ACT_LRELU02 = range(7)
 
 LAUNCHES = [0]  # number of C-ABI launcher calls (bench.py reports it as gpu_launches)
 

@@ -4,7 +4,7 @@ Runs the CPU oracle's train_step (oracle/ha2g_oracle.py, pinned to the unmodifie
 in fp32 (what the reference computes) and in fp64 (what it approximates).  Stores, per parameter tensor, a strided
 sample + norm of the fp64 gradient and the fp32 run's own relative-L2 error against fp64 -- the reference's noise floor:
 the text / audio encoder gradients are ill-conditioned even at B = 128 (2e-3 / 6e-3), the generators' are not (1e-6).
-tests/test_b128_parity.py holds the CUDA step to max(1e-3, 3 x that floor) against the fp64 values.
+tests/test_b128_parity.py holds the CUDA step to max(1e-3, 4 x that floor) against the fp64 values.
 
     python oracle/make_b128_golden.py [expressive gesture]      (~2.5 min per variant on 8 cores)
 Writes tests/golden/b128_<variant>.pt

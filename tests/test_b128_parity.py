@@ -3,7 +3,7 @@ discriminator step + generator step) on the CUDA path -- M = 384-row ride-along 
 streaming contrastive loss -- against the CPU oracle evaluated in fp64 on the same inputs and draws
 (tests/golden/b128_<variant>.pt, written by oracle/make_b128_golden.py together with the fp32 oracle's own error against
 fp64: the reference's noise floor).  Losses are held to the north-star 1e-3; every pre-Adam gradient tensor to
-max(1e-3, 3 x the reference's own fp32 error for that tensor's family) in relative L2 over a strided sample: the
+max(1e-3, 4 x the reference's own fp32 error for that tensor's family) in relative L2 over a strided sample: the
 generators' gradients are well conditioned (reference noise 1e-6 -> bound 1e-3), the text / audio encoders' are not
 even at B = 128 (reference noise 2e-3 / 6e-3)."""
 import os
@@ -63,7 +63,7 @@ def test_step_b128_vs_fp64_oracle(variant):
     mods.update(text=T, audio=A)
     for fam, entry in g["families"].items():
         named = dict(mods[fam].named_parameters())
-        tol = max(1e-3, 3.0 * entry["fp32_ref_worst"])
+        tol = max(1e-3, 4.0 * entry["fp32_ref_worst"])
         for name, rec in entry["tensors"].items():
             summ = rec["summary"]
             mine = sample_tensor(captured[id(named[name])], 512)

@@ -117,3 +117,62 @@ def test_reads_reference_written_checkpoint_and_vice_versa(tmp_path):
             assert k0 == k1 and torch.equal(v0, v1), (k, k0)
     for (k0, v0), (k1, v1) in zip(ck["audio_dict"].items(), out[4].state_dict().items()):
         assert k0 == k1 and torch.equal(v0, v1), k0
+
+
+@pytest.mark.gpu
+def test_resume_reproduces_the_next_step(tmp_path):
+    """Save after two training steps (weights, BatchNorm buffers, Adam moments), resume into freshly built modules and
+    optimizers, and take the third step in both worlds: the step is deterministic, so losses and parameters must agree
+    exactly -- through the eager path and through a re-captured CUDA graph."""
+    from helpers import build_modules
+    from ha2g_b200 import checkpoint, graph_step, rng
+    from ha2g_b200.model.vocab import make_speaker_vocab
+    from ha2g_b200.synthetic import make_batch
+    from ha2g_b200.train_eval.train_hierarchy import train_iter_hierarchy
+    dev = "cuda:0"
+    seeds = {"gens": 20, "dis": 30, "audio": 31, "text": 32}
+
+    def world():
+        args, gens, D, A, T = build_modules("gesture", 60, 5, seeds, dev)
+        lr = args.learning_rate
+        mk = lambda m, l=lr: torch.optim.Adam(m.parameters(), lr=l, betas=(0.5, 0.999))
+        opts = {f"g{k + 1}": mk(g) for k, g in enumerate(gens)}
+        opts.update(dis=mk(D, lr * args.discriminator_lr_weight), audio=mk(A), text=mk(T))
+        return args, gens, D, A, T, opts
+
+    gtor = torch.Generator().manual_seed(5)
+    noise = [torch.randn((4, 16), generator=gtor).to(dev) for _ in range(9)]
+    perm = torch.randperm(4, generator=gtor).to(dev)
+
+    def step(w, i, calls=[0]):
+        args, gens, D, A, T, opts = w
+        b = {k: v.to(dev) for k, v in make_batch("gesture", 4, 60, 5, seed=700 + i).items()}
+        cnt = [0]
+
+        def randn_fn(shape):
+            cnt[0] += 1
+            return noise[(cnt[0] - 1) % 9]
+        with rng.override(randn_fn=randn_fn, randperm_fn=lambda n: perm, dropout=False, graph_safe=True):
+            return train_iter_hierarchy(args, 11, b["in_text_padded"], b["in_spec"], b["target"], b["vid"], *gens, D, A, T,
+                                        *[opts[f"g{k + 1}"] for k in range(3)], opts["dis"], opts["audio"], opts["text"])
+
+    graph_step.reset()
+    graph_step.enable(False)
+    try:
+        w1 = world()
+        for i in range(2):
+            step(w1, i)
+        path = str(tmp_path / "ckpt.bin")
+        checkpoint.save_checkpoint_hierarchy(path, w1[0], 7, None, make_speaker_vocab(5), 27, w1[1], w1[2], w1[3], w1[4],
+                                             optimizers=w1[5])
+        r1 = step(w1, 2)
+        w2 = world()
+        assert checkpoint.resume_training(path, w2[1], w2[2], w2[3], w2[4], optimizers=w2[5]) == 7
+        r2 = step(w2, 2)
+        assert r1 == r2, (r1, r2)
+        for m1, m2 in zip(w1[1] + [w1[2], w1[3], w1[4]], w2[1] + [w2[2], w2[3], w2[4]]):
+            for (n, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+                assert torch.equal(a, b), n
+    finally:
+        graph_step.enable(True)
+        graph_step.reset()

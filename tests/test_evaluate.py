@@ -60,8 +60,6 @@ def test_pose_conversion_and_metrics_match_reference():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HA2G_TEST_EVALUATE_GPU") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a B200 (set HA2G_TEST_EVALUATE_GPU=1)")
 def test_evaluate_testset_runs_and_matches_manual_metrics():
     """The loop on the GPU: outputs of the eval-mode cascade (already pinned module by module) -> the returned dict
     equals the metrics recomputed from the same outputs; modules return to training mode."""
@@ -96,3 +94,29 @@ def test_evaluate_testset_runs_and_matches_manual_metrics():
     for m in gens + [A]:
         m.train(True)
     assert abs(ret["loss"] - np.mean(losses)) < 1e-5
+
+
+@pytest.mark.gpu
+def test_evaluate_testset_with_fgd_evaluator():
+    """evaluate_testset on the TED-Expressive cascade with the CUDA FGD evaluator (MotionAE features + Frechet distance):
+    the returned dict carries frechet / feat_dist / diversity like the reference's (train_expressive.py:609-627)."""
+    import argparse
+    import types
+    from helpers import build_modules
+    from ha2g_b200 import rng
+    from ha2g_b200.model.embedding_space_evaluator import EmbeddingSpaceEvaluator
+    from ha2g_b200.model.motion_ae import MotionAE
+    from ha2g_b200.synthetic import det_fill, make_batch
+    dev = "cuda:0"
+    args, gens, D, A, T = build_modules("expressive", 60, 5, {"gens": 20, "dis": 30, "audio": 31, "text": 32}, dev)
+    ae = det_fill(MotionAE(126, 128), 90)
+    ev = EmbeddingSpaceEvaluator(argparse.Namespace(n_pre_poses=4, n_poses=34, pose_dim=126), None, types.SimpleNamespace(),
+                                 torch.device(dev), ckpt={"pose_dim": 126, "latent_dim": 128, "motion_ae": ae.state_dict()})
+    batches = []
+    for i in range(3):
+        b = make_batch("expressive", 48, 60, 5, seed=60 + i)
+        batches.append((torch.zeros(1), torch.zeros(1), b["in_text_padded"], None, b["target"], torch.zeros(48, 10), b["in_spec"], {}))
+    ret = evaluate.evaluate_testset(batches, None, *gens, A, None, ev, args)
+    assert {"loss", "joint_mae", "frechet", "feat_dist", "diversity"} <= set(ret)
+    assert ev.get_no_of_samples() == 3 and np.isfinite(ret["frechet"]) and ret["frechet"] > 0 and ret["feat_dist"] > 0
+    assert all(m.training for m in gens + [A])
