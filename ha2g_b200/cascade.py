@@ -92,14 +92,20 @@ def split_targets(variant: str, target: torch.Tensor) -> List[torch.Tensor]:
     return [ops.gather_cols(target, t[0]) for t in tabs]
 
 
-def run_cascade(variant: str, gens, targets: List[torch.Tensor], in_text, blends, vid, n_pre: int, eps=None):
+def run_cascade(variant: str, gens, targets: List[torch.Tensor], in_text, blends, vid, n_pre: int, eps=None, text_feats=None):
     """g1 -> ... -> gL with the pre_seq wiring; returns ([out_1..out_L], (z, mu, logvar) of the last level).
-    eps: optional per-level reparameterisation noise drawn by the caller (else each generator draws its own)."""
+    eps: optional per-level reparameterisation noise drawn by the caller (else each generator draws its own);
+    text_feats: optional per-level outputs of the generators' own text encoders, computed ahead of time."""
     tabs = device_tables(variant, targets[0].device)
     outs, prev, last = [], None, None
     for k, g in enumerate(gens):
         pre = ops.pre_seq(targets[k], prev, tabs[k][1], tabs[k][2], n_pre)
-        out, z, mu, lv = g(pre, in_text, blends[k], vid) if eps is None else g(pre, in_text, blends[k], vid, _eps=eps[k])
+        kw = {}
+        if eps is not None:
+            kw["_eps"] = eps[k]
+        if text_feats is not None:
+            kw["_text_feat"] = text_feats[k]
+        out, z, mu, lv = g(pre, in_text, blends[k], vid, **kw)
         outs.append(out)
         prev, last = out, (z, mu, lv)
     return outs, last

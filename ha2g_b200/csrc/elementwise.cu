@@ -649,3 +649,30 @@ HA2G_API int ha2g_place_words(const int64_t* word_id, const double* word_start, 
     place_words_kernel<<<ha2g_div_up(B, 128), 128, 0, stream>>>(word_id, word_start, word_off, clip_start, clip_end, B, n_frames, out);
     HA2G_RETURN_LAST();
 }
+
+namespace {
+// x [W, T, D]: for every window w >= 1 and overlap frame j < n: x[w, j] = x[w-1, T-n+j] * (n-j)/(n+1) + x[w, j] * (j+1)/(n+1).
+// In place: the tails read (frames T-n.. of window w-1) are never written (T > 2n).
+__global__ void crossfade_kernel(float* __restrict__ x, int W, int T, int D, int n) {
+    const int64_t total = (int64_t)(W - 1) * n * D;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const int j = (int)((i / D) % n);
+        const int64_t w = 1 + i / ((int64_t)D * n);
+        const float prev = x[((w - 1) * T + (T - n + j)) * D + d];
+        float* cur = x + (w * T + j) * D + d;
+        *cur = prev * (float)(n - j) / (float)(n + 1) + *cur * (float)(j + 1) / (float)(n + 1);
+    }
+}
+}  // namespace
+
+// Linear cross-fade between consecutive inference windows over their n overlapping frames, all windows at once
+// (scripts/synthesize_expressive_hierarchy.py:195-203: out_seq[j] = last[j] * (n - j) / (n + 1) + out_seq[j] * (j + 1) / (n + 1)).
+// x [W, T, D] holds the raw window outputs; in place.  Requires T > 2 n.
+HA2G_API int ha2g_crossfade(float* x, int W, int T, int D, int n, cudaStream_t stream) {
+    if (W <= 1 || n <= 0) return 0;
+    if (T <= 2 * n) return (int)cudaErrorInvalidValue;
+    const int64_t total = (int64_t)(W - 1) * n * D;
+    crossfade_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(x, W, T, D, n);
+    HA2G_RETURN_LAST();
+}

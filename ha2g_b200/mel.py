@@ -59,8 +59,12 @@ def _device_tables(device):
             else:
                 start.append(int(nz[0]))
                 length.append(int(nz[-1] - nz[0] + 1))
+        n = np.arange(N_FFT, dtype=np.float64)
+        j = np.arange(N_FFT // 2, dtype=np.float64)
+        hann = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / N_FFT)             # periodic Hann (scipy.signal.get_window('hann', 1024))
+        tw = np.concatenate([hann, np.cos(2.0 * np.pi * j / N_FFT), -np.sin(2.0 * np.pi * j / N_FFT)]).astype(np.float32)
         _tables[key] = (torch.from_numpy(fb).to(device), torch.tensor(start, dtype=torch.int32, device=device),
-                        torch.tensor(length, dtype=torch.int32, device=device))
+                        torch.tensor(length, dtype=torch.int32, device=device), torch.from_numpy(tw).to(device))
     return _tables[key]
 
 
@@ -79,9 +83,9 @@ def extract_melspectrogram(y: torch.Tensor, n_out: int | None = None) -> torch.T
     B, n = y2.shape
     frames = 1 + n // HOP
     n_out = frames if n_out is None else n_out
-    fb, st, ln = _device_tables(y2.device)
+    fb, st, ln, tw = _device_tables(y2.device)
     melpow = torch.empty((B, N_MELS, frames), device=y2.device, dtype=torch.float32)
     cmax = torch.empty((B,), device=y2.device, dtype=torch.int32)
     out = torch.empty((B, N_MELS, n_out), device=y2.device, dtype=torch.float32)
-    _call("ha2g_logmel", _p(y2), B, n, _p(fb), _p(st), _p(ln), _p(melpow), _p(cmax), _p(out), n_out, _st())
+    _call("ha2g_logmel", _p(y2), B, n, _p(fb), _p(st), _p(ln), _p(tw), _p(melpow), _p(cmax), _p(out), n_out, _st())
     return out[0] if squeeze else out

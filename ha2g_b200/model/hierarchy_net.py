@@ -227,9 +227,11 @@ class Hierarchical_PoseGenerator(nn.Module):
                                   _LinearP(self.hidden_size // 2, pose_dim)])
         self.do_flatten_parameters = False
 
-    def forward(self, pre_seq, in_text, audio_feat_seq=None, vid_indices=None, _eps=None):
-        # _eps (not part of the reference signature): reparameterisation noise drawn by the caller
-        text_feat_seq = self.text_encoder(in_text)
+    def forward(self, pre_seq, in_text, audio_feat_seq=None, vid_indices=None, _eps=None, _text_feat=None):
+        # _eps / _text_feat (not part of the reference signature): reparameterisation noise drawn by the caller, and the
+        # output of this generator's own text encoder computed ahead of time (the inference loop batches it over all
+        # windows of a clip: it depends on the tokens only)
+        text_feat_seq = self.text_encoder(in_text) if _text_feat is None else _text_feat
         assert audio_feat_seq.shape[1] == text_feat_seq.shape[1]
         assert vid_indices is not None
         z_context = self.speaker_embedding[1](self.speaker_embedding[0](vid_indices))

@@ -105,33 +105,56 @@ def generate_gestures_hierarchy(args, *rest, audio_sr=16000, vid=None, fade_out=
 
     targets = [t.to(dev).float() for t in targets]
     tabs = cascade.device_tables(variant, dev)
+    W = len(plan)
+    n_mel = spectrogram.shape[0]
+
+    # ---- everything that does NOT depend on the previous window, for ALL windows at once -----------------------------
+    # The window chain is serial only through the seed frames.  The audio encoder sees (spectrogram slice, speaker) and
+    # the generators' text encoders see the tokens: both are evaluated here as batches over the clip's windows (eval-mode
+    # BatchNorm is per-sample, so a window's features do not depend on its batch mates) instead of once per window at
+    # batch 1 inside the loop -- the loop body keeps only the recurrent decoders.
+    starts = [p[2] for p in plan]
+    if starts[-1] + spec_len > spectrogram.shape[1]:   # the reference would fail on a short slice too; keep the error explicit
+        raise RuntimeError(f"spectrogram window {W - 1} has {spectrogram.shape[1] - starts[-1]} frames, expected {spec_len}")
+    win_idx = (torch.tensor(starts, device=dev).view(W, 1) + torch.arange(spec_len, device=dev).view(1, spec_len)).reshape(-1)
+    spec_all = spectrogram.index_select(1, win_idx).reshape(n_mel, W, spec_len).permute(1, 0, 2).contiguous()   # [W,128,70]
+    text_all = torch.from_numpy(np.stack([place_words(words, p[0], p[1], n_frames, lang_model) for p in plan])).to(dev)
+    a0 = math.floor(plan[-1][0] / clip_length * len(audio))
+    if len(audio) - a0 < audio_sample_length:
+        end_padding_duration = audio_sample_length - max(0, len(audio) - a0)
+    vid_all = vid_t.expand(W).contiguous()
+    CH = 128                                            # windows per encoder batch (bounds the activation memory)
+    blends_all = [[] for _ in range(L)]
+    text_feat_all = [[] for _ in range(L)]
+    for c0 in range(0, W, CH):
+        sl = slice(c0, min(W, c0 + CH))
+        _, _, _, _, bl = audio_encoder(spec_all[sl], vid_all[sl])
+        for k in range(L):
+            blends_all[k].append(bl[k])
+            text_feat_all[k].append(gens[k].text_encoder(text_all[sl]))
+    # [W, 2L, 34, 32]: per window the L blended audio features then the L text features (one copy per window below)
+    feats_all = torch.stack([torch.cat(x) for x in blends_all] + [torch.cat(x) for x in text_feat_all], dim=1).contiguous()
+
     # static buffers of the window body (also what a captured graph reads and writes)
-    s_spec = torch.empty((1, spectrogram.shape[0], spec_len), device=dev, dtype=torch.float32)
-    s_text = torch.empty((1, n_frames), device=dev, dtype=torch.int64)
+    s_feats = torch.empty((2 * L, 1, n_frames, 32), device=dev, dtype=torch.float32)
+    s_blend = [s_feats[k] for k in range(L)]
+    s_tfeat = [s_feats[L + k] for k in range(L)]
+    s_text = torch.zeros((1, n_frames), device=dev, dtype=torch.int64)   # (unused by the generators once _text_feat is given)
     s_out = torch.zeros((1, n_frames, pose_dim), device=dev, dtype=torch.float32)
+    out_all = torch.empty((W, n_frames, pose_dim), device=dev, dtype=torch.float32)
 
     def body(with_seed: bool):
         if with_seed:  # seed frames: the previous window's last n_pre outputs, per level (:117-125)
             seed = s_out[:, -n_pre:, :].contiguous()
             for k in range(L):
                 targets[k][:, 0:n_pre, :] = ops.gather_cols(seed, tabs[k][0])
-        _, _, _, _, linear_blend_feat = audio_encoder(s_spec, vid_t)
-        outs, _ = cascade.run_cascade(variant, gens, targets, s_text, linear_blend_feat, vid_t, n_pre)
+        outs, _ = cascade.run_cascade(variant, gens, targets, s_text, s_blend, vid_t, n_pre, text_feats=s_tfeat)
         s_out.copy_(outs[-1])
 
-    use_graph = _GRAPH and not rng.overridden() and len(plan) >= 4 and not torch.cuda.is_current_stream_capturing()
+    use_graph = _GRAPH and not rng.overridden() and W >= 4 and not torch.cuda.is_current_stream_capturing()
     graph = None
-    chunks: List[torch.Tensor] = []
-    for i, (start_time, end_time, spec_start) in enumerate(plan):
-        sl = spectrogram[:, spec_start:spec_start + spec_len]
-        if sl.shape[1] == spec_len:
-            s_spec[0].copy_(sl)
-        else:   # the reference would fail on a short slice too; keep the error explicit
-            raise RuntimeError(f"spectrogram window {i} has {sl.shape[1]} frames, expected {spec_len}")
-        a0 = math.floor(start_time / clip_length * len(audio))
-        if len(audio) - a0 < audio_sample_length and i == len(plan) - 1:
-            end_padding_duration = audio_sample_length - max(0, len(audio) - a0)
-        s_text.copy_(torch.from_numpy(place_words(words, start_time, end_time, n_frames, lang_model)).unsqueeze(0))
+    for i in range(W):
+        s_feats.copy_(feats_all[i].unsqueeze(1))
         if use_graph and i == 2:   # windows 0 and 1 ran eagerly (both variants of the body are warm): capture the seeded body
             ops._ensure_workspace()
             torch.cuda.synchronize(dev)
@@ -142,14 +165,13 @@ def generate_gestures_hierarchy(args, *rest, audio_sr=16000, vid=None, fade_out=
             graph.replay()
         else:
             body(i > 0)
-        out_seq = s_out[0].clone()
-        if chunks:  # linear cross-fade over the overlapping n_pre frames (:195-203)
-            last = chunks[-1][-n_pre:]
-            chunks[-1] = chunks[-1][:-n_pre]
-            n = last.shape[0]
-            j = torch.arange(n, device=dev, dtype=torch.float32).unsqueeze(1)
-            out_seq[:n] = last * (n - j) / (n + 1) + out_seq[:n] * (j + 1) / (n + 1)
-        chunks.append(out_seq)
+        out_all[i].copy_(s_out[0])
+
+    # linear cross-fade over the overlapping n_pre frames (:195-203), all windows at once on the device: window i keeps
+    # its frames [0, n_frames - n_pre) (the last window all of them) and its first n_pre frames are blended with the
+    # previous window's last n_pre
+    ops._call("ha2g_crossfade", ops._p(out_all), W, n_frames, pose_dim, n_pre, ops._st())
+    chunks = [out_all[:-1, :n_frames - n_pre].reshape(-1, pose_dim), out_all[-1]]
 
     result = torch.cat(chunks, dim=0).cpu().numpy()
 
