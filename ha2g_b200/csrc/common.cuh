@@ -92,13 +92,15 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh /* >= 33 doub
 
 // activation codes shared by gemm epilogues and element-wise kernels
 enum { HA2G_ACT_NONE = 0, HA2G_ACT_RELU = 1, HA2G_ACT_LRELU = 2, HA2G_ACT_ELU = 3, HA2G_ACT_SIGMOID = 4, HA2G_ACT_TANH = 5,
-       HA2G_ACT_LRELU02 = 6 /* LeakyReLU(0.2): the FGD auto-encoder, scripts/model/motion_ae.py:21,26 */ };
+       HA2G_ACT_LRELU02 = 6 /* LeakyReLU(0.2): the FGD auto-encoder, scripts/model/motion_ae.py:21,26 */,
+       HA2G_ACT_LRELU03 = 7 /* LeakyReLU(0.3): the baseline WavEncoder, scripts/model/multimodal_context_net.py:15,18,21 */ };
 
 __device__ __forceinline__ float ha2g_act(float x, int act) {
     switch (act) {
         case HA2G_ACT_RELU: return x > 0.f ? x : 0.f;
         case HA2G_ACT_LRELU: return x > 0.f ? x : 0.01f * x;
         case HA2G_ACT_LRELU02: return x > 0.f ? x : 0.2f * x;
+        case HA2G_ACT_LRELU03: return x > 0.f ? x : 0.3f * x;
         case HA2G_ACT_ELU: return x > 0.f ? x : expm1f(x);
         case HA2G_ACT_SIGMOID: return ha2g_sigmoid(x);
         case HA2G_ACT_TANH: return tanhf(x);
@@ -111,6 +113,7 @@ __device__ __forceinline__ float ha2g_act_grad_from_out(float y, int act) {
         case HA2G_ACT_RELU: return y > 0.f ? 1.f : 0.f;
         case HA2G_ACT_LRELU: return y > 0.f ? 1.f : 0.01f;
         case HA2G_ACT_LRELU02: return y > 0.f ? 1.f : 0.2f;
+        case HA2G_ACT_LRELU03: return y > 0.f ? 1.f : 0.3f;
         case HA2G_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
         case HA2G_ACT_SIGMOID: return y * (1.f - y);
         case HA2G_ACT_TANH: return 1.f - y * y;

@@ -676,3 +676,54 @@ HA2G_API int ha2g_crossfade(float* x, int W, int T, int D, int n, cudaStream_t s
     crossfade_kernel<<<ha2g_ew_grid(total), 256, 0, stream>>>(x, W, T, D, n);
     HA2G_RETURN_LAST();
 }
+
+namespace {
+// out[b,to,k*C+c] = x[b, to*stride - pad + k, c] (0 outside [0,T))
+__global__ void unfold1d_strided_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t B, int T, int C,
+                                            int Kw, int stride, int pad, int To) {
+    const int W = Kw * C;
+    const int64_t n = B * To * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int kc = (int)(i % W);
+        const int64_t bt = i / W;
+        const int to = (int)(bt % To);
+        const int64_t b = bt / To;
+        const int k = kc / C, c = kc % C;
+        const int t = to * stride - pad + k;
+        out[i] = (t >= 0 && t < T) ? x[(b * T + t) * C + c] : 0.f;
+    }
+}
+// dx[b,t,c] = sum over (to, k) with to*stride - pad + k == t of dout[b,to,k*C+c]   (gather form: no atomics)
+__global__ void unfold1d_strided_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int64_t B, int T, int C,
+                                            int Kw, int stride, int pad, int To) {
+    const int W = Kw * C;
+    const int64_t n = B * T * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t bt = i / C;
+        const int t = (int)(bt % T);
+        const int64_t b = bt / T;
+        float v = 0.f;
+        // k = t + pad - to*stride in [0, Kw)  <=>  to in [ceil((t + pad - Kw + 1) / stride), floor((t + pad) / stride)]
+        const int hi = min(To - 1, (t + pad) / stride);
+        int lo = t + pad - Kw + 1;
+        lo = lo <= 0 ? 0 : (lo + stride - 1) / stride;
+        for (int to = lo; to <= hi; ++to) {
+            const int k = t + pad - to * stride;
+            v += dout[(b * To + to) * W + k * C + c];
+        }
+        dx[i] = v;
+    }
+}
+}  // namespace
+
+// Strided, zero-padded Conv1d input staging (im2col) for the baseline WavEncoder (multimodal_context_net.py:13-22):
+// x [B,T,C] -> out [B,To,Kw*C], To = (T + 2*pad - Kw)/stride + 1
+HA2G_API int ha2g_unfold1d_strided_fwd(const float* x, float* out, int64_t B, int T, int C, int Kw, int stride, int pad,
+                                       int To, cudaStream_t stream) {
+    EW_LAUNCH(unfold1d_strided_fwd_kernel, B * To * Kw * C, x, out, B, T, C, Kw, stride, pad, To);
+}
+HA2G_API int ha2g_unfold1d_strided_bwd(const float* dout, float* dx, int64_t B, int T, int C, int Kw, int stride, int pad,
+                                       int To, cudaStream_t stream) {
+    EW_LAUNCH(unfold1d_strided_bwd_kernel, B * T * C, dout, dx, B, T, C, Kw, stride, pad, To);
+}

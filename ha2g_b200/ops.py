@@ -14,7 +14,7 @@ import torch
 from ._lib import lib
 from . import rng as _rng
 
-ACT_NONE, ACT_RELU, ACT_LRELU, ACT_ELU, ACT_SIGMOID, ACT_TANH, ACT_LRELU02 = range(7)
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_ELU, ACT_SIGMOID, ACT_TANH, ACT_LRELU02, ACT_LRELU03 = range(8)
 
 LAUNCHES = [0]  # number of C-ABI launcher calls (bench.py reports it as gpu_launches)
 
@@ -736,6 +736,38 @@ class _PackConv1dWFn(torch.autograd.Function):
         dw = torch.empty((O, I, Kw), device=dwp.device, dtype=torch.float32)
         _call("ha2g_pack_conv1d_w", _p(dwp), _p(dw), O, I, Kw, 1, _st())
         return dw
+
+
+class _Unfold1dStridedFn(torch.autograd.Function):
+    """im2col of a strided, zero-padded Conv1d on a channels-last sequence: x [B,T,C] -> [B,To,Kw*C]."""
+
+    @staticmethod
+    def forward(ctx, x, kw, stride, pad):
+        x = _c(x)
+        _chk(x)
+        B, T, C = x.shape
+        To = (T + 2 * pad - kw) // stride + 1
+        out = torch.empty((B, To, kw * C), device=x.device, dtype=torch.float32)
+        _call("ha2g_unfold1d_strided_fwd", _p(x), _p(out), B, T, C, kw, stride, pad, To, _st())
+        ctx.cfg = (B, T, C, kw, stride, pad, To)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, C, kw, stride, pad, To = ctx.cfg
+        dout = _c(dout)
+        dx = torch.empty((B, T, C), device=dout.device, dtype=torch.float32)
+        _call("ha2g_unfold1d_strided_bwd", _p(dout), _p(dx), B, T, C, kw, stride, pad, To, _st())
+        return dx, None, None, None
+
+
+def conv1d(x, w, b, stride=1, pad=0, act=ACT_NONE):
+    """nn.Conv1d(C_in, C_out, Kw, stride, padding) on a [B,T,C_in] (channels-last) sequence -> [B,To,C_out]
+    (the baseline WavEncoder's k = 15, stride 5 / 6 convolutions, multimodal_context_net.py:13-22)."""
+    kw = w.shape[2]
+    if stride == 1 and pad == 0:
+        return conv1d_valid(x, w, b, act)
+    return linear(_Unfold1dStridedFn.apply(x, kw, stride, pad), _PackConv1dWFn.apply(w), b, act)
 
 
 def conv1d_valid(x, w, b, act=ACT_NONE):

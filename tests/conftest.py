@@ -16,7 +16,7 @@ def pytest_configure(config):
 # Unit-level parity first, whole-step machinery last: with `-x` a failure in the CUDA-graph tests must not hide the kernel,
 # mel and inference tests behind it.
 _ORDER = ["test_boundary", "test_oracle_pinned", "test_mel", "test_kernels", "test_gpu_parity", "test_synthesize",
-          "test_evaluate", "test_fgd", "test_pipeline", "test_checkpoint", "test_data", "test_dp_gloo", "test_dp_nccl", "test_b128_parity",
+          "test_evaluate", "test_fgd", "test_pipeline", "test_gan_baseline", "test_checkpoint", "test_data", "test_dp_gloo", "test_dp_nccl", "test_b128_parity",
           "test_graph_step"]
 
 
