@@ -151,27 +151,28 @@ def step_flops(variant, B, epoch_full=True):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def gru_kernel_roofline(dev, M, T=T_FRAMES, H=300, iters=24):
+def gru_kernel_roofline(dev, M, M_gates, T=T_FRAMES, H=300, iters=24):
     """Live CUDA-event timing of the fused GRU recurrence kernel (the kernel the north star names) at the shape the step
-    launches it with, rotating over buffer sets larger than the 126 MB L2 between launches.
-    -> (average launch ms, algorithmic FLOPs per launch, algorithmic bytes per launch)."""
+    launches it with (M rows of which the first M_gates save their gates), rotating over buffer sets larger than the
+    126 MB L2 between launches.  -> (average launch ms, algorithmic FLOPs per launch, algorithmic bytes per launch, ...)."""
     import torch
     from ha2g_b200._lib import lib
     from ha2g_b200 import ops
     ops._ensure_workspace()
     st = torch.cuda.current_stream().cuda_stream
-    per_set = M * T * (6 * H + 2 * H + 8 * H) * 4
+    per_set = (M * T * (6 * H + 2 * H) + M_gates * T * 8 * H) * 4     # gi read + y written + saved gates written
     nsets = max(2, int(140e6 // per_set) + 1)
     sets = []
     for _ in range(nsets):
-        sets.append((torch.randn(M, T, 6 * H, device=dev), torch.empty(M, T, 2 * H, device=dev), torch.empty(M, T, 8 * H, device=dev)))
+        sets.append((torch.randn(M, T, 6 * H, device=dev), torch.empty(M, T, 2 * H, device=dev),
+                     torch.empty(max(M_gates, 1), T, 8 * H, device=dev)))
     w = [torch.randn(3 * H, H, device=dev) * 0.05 for _ in range(2)]
     b = [torch.randn(3 * H, device=dev) * 0.05 for _ in range(2)]
     p = lambda t: t.data_ptr()
 
     def launch(i):
         gi, y, gates = sets[i % len(sets)]
-        rc = lib.ha2g_gru_seq_fwd_tc2(p(gi), p(w[0]), p(w[1]), p(b[0]), p(b[1]), p(y), p(gates), M, M, T, H, st)
+        rc = lib.ha2g_gru_seq_fwd_tc2(p(gi), p(w[0]), p(w[1]), p(b[0]), p(b[1]), p(y), p(gates) if M_gates else None, M, M_gates, T, H, st)
         assert rc is None or rc == 0
     for i in range(4):
         launch(i)
@@ -503,8 +504,10 @@ def main_train(a, rank, world, local_rank):
         step(i, False)
     barrier()
     topstat = ops.profile_end().get(top, None)
-    gru_M = ops.gru_rows_per_launch(a.batch, a.epoch > args.loss_warmup) if hasattr(ops, "gru_rows_per_launch") else a.batch
-    kern = gru_kernel_roofline(dev, gru_M) if rank == 0 else None
+    # the step's cascade runs once over [G; D; R] rows (ops.ride_along): M = 3B rows per launch (2B before the GAN warm-up
+    # ends), gates saved for the B differentiated rows
+    gru_M = a.batch * (3 if a.epoch > args.loss_warmup and args.loss_gan_weight > 0 else 2)
+    kern = gru_kernel_roofline(dev, gru_M, a.batch) if rank == 0 else None
     if rank != 0:
         _finish_process(world)
         return
@@ -518,7 +521,7 @@ def main_train(a, rank, world, local_rank):
     peak_burst_src = ("measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback (B200_PROFILING.md 1.59 PF burst)")
     traffic, traffic_src = ncu_traffic(f"gru_seq_fwd_tc2_kernel_M{gru_M}")
     roofline = {"bound": "tensor", "kernel": "gru_seq_fwd_tc2_kernel (csrc/gru_cluster_tc2.cu), one bidirectional GRU layer, "
-                                             f"M={gru_M} rows x T=34 x H=300",
+                                             f"M={gru_M} rows (gates saved for {a.batch}) x T=34 x H=300",
                 "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": kern_bytes,
                 "peak_source": peak_burst_src, "us_per_launch": kern_ms * 1e3, "flops_per_launch": kern_flops,

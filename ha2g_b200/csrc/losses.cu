@@ -246,142 +246,133 @@ __global__ void physical_kernel(const float* __restrict__ out, float* __restrict
 }
 
 // ---- contrastive --------------------------------------------------------------------------------------
+// SoftmaxContrastiveLoss on the tensor cores.  Rows are L2-normalised, so the pairwise distances come from ONE Gram
+// matrix  G = an bn^T  (K = 32: the packed tcgen05 GEMM of gemm_tc2.cu, bf16x3):  D_ij^2 = |an_i|^2 + |bn_j|^2 - 2 G_ij.
+// Where that difference cancels (D^2 < 0.25: close pairs, e.g. trained positives) the entry is recomputed from the direct
+// differences, so the logits 1/D keep the reference's behaviour near coincident rows.  Everything after the Gram matrix
+// is row-local:   logits + online log-sum-exp (one CTA per row)  ->  loss;
+// backward:       C_ij = d loss / d D_ij / D_ij  written over the logits (one CTA per row, row sums on the way),
+//                 column sums (ordered two-stage reduction),  X = C bn  and  Y = C^T an  (two more tcgen05 GEMMs, K = N),
+//                 da_i = rs_i an_i - X_i,  db_j = cs_j bn_j - Y_j,  then the L2-normalisation backward.
+// One pass over the N x N matrix per stage instead of three 32-wide SIMT sweeps; no atomics anywhere (deterministic).
 constexpr int CC = 32;      // feature width (nOut of both encoders)
-constexpr int CT = 128;     // rows per CTA / tile
+constexpr float CLOSE_D2 = 0.25f;
 
-// xn = x / max(|x|, 1e-12), norms saved.   one warp per row, lane = channel
-__global__ void l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ nrm, int64_t N) {
+// xn = x / max(|x|, 1e-12), norms and |xn|^2 saved.   one warp per row, lane = channel
+__global__ void l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ nrm,
+                                   float* __restrict__ sq, int64_t N) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (row >= N) return;
     float v = x[row * CC + lane];
     float s = warp_sum(v * v);
     float n = fmaxf(sqrtf(s), 1e-12f);
-    xn[row * CC + lane] = v / n;
-    if (lane == 0) nrm[row] = n;
-}
-// dx = (dn - (dn . n) n) / norm, with dn = the sum of `planes` partial planes [planes][N][32] added in index order (the
-// column splits of contrastive_pair_kernel<1> each write their own plane: no atomics)
-__global__ void l2norm_rows_bwd_kernel(const float* __restrict__ dn, int planes, const float* __restrict__ xn,
-                                       const float* __restrict__ nrm, float* __restrict__ dx, int64_t N) {
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-    const int lane = threadIdx.x % 32;
-    if (row >= N) return;
-    float g = 0.f;
-    for (int p = 0; p < planes; ++p) g += dn[((size_t)p * N + row) * CC + lane];
-    const float n = xn[row * CC + lane];
-    float dot = warp_sum(g * n);
-    dx[row * CC + lane] = (g - dot * n) / nrm[row];
+    const float u = v / n;
+    xn[row * CC + lane] = u;
+    const float q = warp_sum(u * u);
+    if (lane == 0) { nrm[row] = n; sq[row] = q; }
 }
 
 __device__ __forceinline__ float contrastive_logit(float d, int variant) {
     return variant == 0 ? fmaxf(1.0f / (d + 1e-8f), 1e-8f) : 1.0f / d;
 }
 
-// MODE 0: forward partial (max, sumexp) of row i over the column split -> part[i][split][2]; diag logit -> diag[i]
-// MODE 1: gradient wrt the OWNED rows (rows of `own`), other side streamed.  own_is_a: owned rows are a (loss rows i)
-//         da_i += sum_j c_ij (a_i - b_j)      c_ij = gs * (p_ij - delta_ij) * dl/dD / D,   p_ij = exp(l_ij - lse_i)
-//         (own_is_a == 0): db_j += sum_i c_ij (b_j - a_i)
-template <int MODE>
-__global__ void __launch_bounds__(CT, 4) contrastive_pair_kernel(const float* __restrict__ own, const float* __restrict__ oth,
-                                                              const float* __restrict__ lse, float* __restrict__ part,
-                                                              float* __restrict__ diag, float* __restrict__ dgrad,
-                                                              const float* __restrict__ gscale, int N, int variant,
-                                                              int own_is_a, int cols_per_split, int Noth, int off) {
-    // rectangular form (data-parallel global batch): `own` has N rows, `oth` has Noth rows; the loss rows are always the
-    // rows of a, whose label is column (row + off) of b.  Square single-GPU case: Noth == N, off == 0.
-    // every lane of a warp reads the SAME tile row (its own row of `own` lives in registers): unpadded rows, 128-bit
-    // broadcast loads -- 8 LDS.128 per pair instead of 32 LDS.32
-    __shared__ __align__(16) float tile[CT][CC];
-    __shared__ float tlse[CT];
-    const int i = blockIdx.x * CT + threadIdx.x;
-    const bool valid = i < N;
-    float me[CC];
-#pragma unroll
-    for (int c = 0; c < CC; ++c) me[c] = valid ? own[(size_t)i * CC + c] : 0.f;
-    const int j_beg = blockIdx.y * cols_per_split, j_end = min(Noth, j_beg + cols_per_split);
-    const int Na = own_is_a ? N : Noth;   // number of loss rows (rows of a)
+// One CTA per loss row i: G[i, :] (Gram entries) -> logits (in place), lse[i], rowloss[i] = lse_i - l_{i, i+off}
+__global__ void __launch_bounds__(256) contrastive_rows_kernel(float* __restrict__ G, const float* __restrict__ an,
+                                                               const float* __restrict__ bn, const float* __restrict__ sqa,
+                                                               const float* __restrict__ sqb, float* __restrict__ lse,
+                                                               float* __restrict__ rowloss, int Nb, int off, int variant) {
+    __shared__ float arow[CC];
+    __shared__ float shm[8], shs[8];
+    __shared__ float sdiag;
+    const int i = blockIdx.x, tid = threadIdx.x;
+    if (tid < CC) arow[tid] = an[(size_t)i * CC + tid];
+    __syncthreads();
+    const float qa = sqa[i];
+    float* g = G + (size_t)i * Nb;
     float m = -CUDART_INF_F, s = 0.f;
-    float acc[CC];
-    float my_lse = 0.f, gs = 0.f;
-    if (MODE == 1) {
+    for (int j = tid; j < Nb; j += 256) {
+        float d2 = qa + sqb[j] - 2.f * g[j];
+        if (d2 < CLOSE_D2) {   // cancellation zone: direct differences, as the reference computes every pair
+            const float* br = bn + (size_t)j * CC;
+            d2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < CC; ++c) acc[c] = 0.f;
-        gs = (gscale != nullptr ? *gscale : 1.f) / (float)Na;
-        if (own_is_a && valid) my_lse = lse[i];
+            for (int c = 0; c < CC; ++c) { const float df = arow[c] - br[c]; d2 = fmaf(df, df, d2); }
+        }
+        const float l = contrastive_logit(sqrtf(fmaxf(d2, 0.f)), variant);
+        g[j] = l;
+        if (j == i + off) sdiag = l;
+        if (l > m) { s = s * expf(m - l) + 1.f; m = l; }
+        else s += expf(l - m);
     }
-    for (int j0 = j_beg; j0 < j_end; j0 += CT) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < CT * CC / 4; e += CT) {   // 16-byte coalesced copies ([N,32] fp32 rows are 128 B)
-            const int r = e / (CC / 4), c4 = e % (CC / 4);
-            const int j = j0 + r;
-            reinterpret_cast<float4*>(&tile[r][0])[c4] =
-                j < j_end ? reinterpret_cast<const float4*>(oth + (size_t)j * CC)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (MODE == 1 && !own_is_a) {
-            int j = j0 + threadIdx.x;
-            tlse[threadIdx.x] = j < j_end ? lse[j] : 0.f;
-        }
-        __syncthreads();
-        if (!valid) continue;
-        const int cnt = min(CT, j_end - j0);
-        for (int r = 0; r < cnt; ++r) {
-            float t[CC];
+    // combine (max, sum-exp) over the block in a fixed order: lanes by shuffle tree, then the 8 warps in index order
 #pragma unroll
-            for (int c4 = 0; c4 < CC / 4; ++c4) {
-                const float4 v = reinterpret_cast<const float4*>(&tile[r][0])[c4];
-                t[c4 * 4] = v.x; t[c4 * 4 + 1] = v.y; t[c4 * 4 + 2] = v.z; t[c4 * 4 + 3] = v.w;
-            }
-            float d2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < CC; ++c) { float df = me[c] - t[c]; d2 = fmaf(df, df, d2); }
-            const float d = sqrtf(d2);
-            const float l = contrastive_logit(d, variant);
-            const int j = j0 + r;
-            const bool is_diag = own_is_a ? (j == i + off) : (j + off == i);
-            if (MODE == 0) {
-                if (is_diag) diag[i] = l;
-                if (l > m) { s = s * expf(m - l) + 1.f; m = l; }
-                else s += expf(l - m);
-            } else {
-                const float row_lse = own_is_a ? my_lse : tlse[r];
-                float p = expf(l - row_lse);
-                if (is_diag) p -= 1.f;
-                float dld;
-                if (variant == 0) { float t = d + 1e-8f; dld = -1.f / (t * t); }
-                else dld = -1.f / (d * d);
-                float cf = d > 0.f ? gs * p * dld / d : 0.f;
-#pragma unroll
-                for (int c = 0; c < CC; ++c) acc[c] = fmaf(cf, me[c] - t[c], acc[c]);
-            }
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, o), so = __shfl_xor_sync(0xffffffffu, s, o);
+        const float mm = fmaxf(m, mo);
+        const float sa = (m == -CUDART_INF_F) ? 0.f : s * expf(m - mm), sb = (mo == -CUDART_INF_F) ? 0.f : so * expf(mo - mm);
+        // both halves of a pair must compute the identical value: order the operands by lane parity of the exchange
+        const bool low = ((threadIdx.x & o) == 0);
+        s = low ? sa + sb : sb + sa;
+        m = mm;
     }
-    if (!valid) return;
-    if (MODE == 0) {
-        part[((size_t)i * gridDim.y + blockIdx.y) * 2 + 0] = m;
-        part[((size_t)i * gridDim.y + blockIdx.y) * 2 + 1] = s;
-    } else {
-#pragma unroll
-        for (int c = 0; c < CC; ++c) dgrad[((size_t)blockIdx.y * N + i) * CC + c] = acc[c];
+    if ((tid & 31) == 0) { shm[tid >> 5] = m; shs[tid >> 5] = s; }
+    __syncthreads();
+    if (tid == 0) {
+        float mm = -CUDART_INF_F;
+        for (int w = 0; w < 8; ++w) mm = fmaxf(mm, shm[w]);
+        float ss = 0.f;
+        for (int w = 0; w < 8; ++w) ss += (shm[w] == -CUDART_INF_F) ? 0.f : shs[w] * expf(shm[w] - mm);
+        const float l = mm + logf(ss);
+        lse[i] = l;
+        rowloss[i] = l - sdiag;
     }
 }
 
-// lse_i from the split partials; loss += mean_i (lse_i - l_ii)
-__global__ void contrastive_finalize_kernel(const float* __restrict__ part, const float* __restrict__ diag, int N, int S,
-                                            float* __restrict__ lse, float* __restrict__ loss) {
+// loss += mean(rowloss) with a fixed summation pattern (one CTA)
+__global__ void __launch_bounds__(1024) contrastive_mean_kernel(const float* __restrict__ rowloss, int N, float* __restrict__ loss) {
     __shared__ float sh[33];
     float acc = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        float m = -CUDART_INF_F;
-        for (int k = 0; k < S; ++k) m = fmaxf(m, part[((size_t)i * S + k) * 2]);
-        float s = 0.f;
-        for (int k = 0; k < S; ++k) s += part[((size_t)i * S + k) * 2 + 1] * expf(part[((size_t)i * S + k) * 2] - m);
-        float l = m + logf(s);
-        lse[i] = l;
-        acc += l - diag[i];
+    for (int i = threadIdx.x; i < N; i += 1024) acc += rowloss[i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) *loss += acc / (float)N;
+}
+
+// One CTA per loss row i: logits -> C_ij = gs (p_ij - delta_ij) (dl/dD) / D   (in place), rs[i] = sum_j C_ij
+__global__ void __launch_bounds__(256) contrastive_coef_kernel(float* __restrict__ G, const float* __restrict__ lse,
+                                                               const float* __restrict__ gscale, float* __restrict__ rs,
+                                                               int Na, int Nb, int off, int variant) {
+    __shared__ float sh[33];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const float gs = (gscale != nullptr ? *gscale : 1.f) / (float)Na;
+    const float li = lse[i];
+    float* g = G + (size_t)i * Nb;
+    float acc = 0.f;
+    for (int j = tid; j < Nb; j += 256) {
+        const float l = g[j];
+        float p = expf(l - li);
+        if (j == i + off) p -= 1.f;
+        // D and dl/dD from the stored logit: expressive l = 1/D; gesture l = 1/(D + 1e-8)  (its clamp at 1e-8 is never
+        // active for D <= 2).  dl/dD = -l^2 in both; coincident rows (D = 0) contribute no gradient, as before.
+        const float d = variant == 0 ? 1.0f / l - 1e-8f : 1.0f / l;
+        const float cf = (d > 0.f && isfinite(l)) ? gs * p * (-l * l) / d : 0.f;
+        g[j] = cf;
+        acc += cf;
     }
     acc = block_sum(acc, sh);
-    grid_accumulate(acc / (float)N, loss);
+    if (tid == 0) rs[i] = acc;
+}
+
+// dn = sc[row] * xn[row] - P[row];  dx = (dn - (dn . xn) xn) / norm        (one warp per row, lane = channel)
+__global__ void contrastive_finish_kernel(const float* __restrict__ sc, const float* __restrict__ xn, const float* __restrict__ P,
+                                          const float* __restrict__ nrm, float* __restrict__ dx, int64_t N) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= N) return;
+    const float n = xn[row * CC + lane];
+    const float g = sc[row] * n - P[row * CC + lane];
+    const float dot = warp_sum(g * n);
+    dx[row * CC + lane] = (g - dot * n) / nrm[row];
 }
 
 }  // namespace
@@ -437,73 +428,47 @@ HA2G_API int ha2g_physical(const float* out, float* grad, int64_t rows, int vari
     physical_kernel<<<ha2g_div_up(rows, 4), 128, 0, stream>>>(out, grad, rows, variant, nb, npairs, loss);
     HA2G_RETURN_LAST();
 }
-extern "C" int ha2g_contrastive_fwd_rect(const float*, const float*, float*, float*, float*, float*, float*, float*, float*,
-                                         int, int, int, int, float*, cudaStream_t);
-extern "C" int ha2g_contrastive_bwd_rect(const float*, const float*, const float*, const float*, const float*, const float*,
-                                         float*, float*, float*, float*, int, int, int, int, cudaStream_t);
-// Rectangular SoftmaxContrastiveLoss for the data-parallel global batch (the reference computes the loss over the whole
-// DataParallel batch, scripts/train_expressive.py:184-197 + train_hierarchy_expressive.py:244-249): a [Na,32] are this
-// rank's rows, b [Nb,32] the all-gathered columns, row i's positive is column i + off (off = rank * Na).
-// loss ACCUMULATED += mean over the Na local rows.  part: [Na * ceil(Nb/128) * 2] floats (upper bound), diag/lse/na: [Na],
-// an [Na,32], bn [Nb,32], nb [Nb].
+extern "C" int ha2g_gemm(const float*, const float*, float*, const float*, int, int, int, int, int, int, int, int, int, int, int,
+                         cudaStream_t);
+extern "C" int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
+
+// Rectangular SoftmaxContrastiveLoss forward (also the data-parallel global-batch form: the reference computes the loss
+// over the whole DataParallel batch, scripts/train_expressive.py:184-197 + train_hierarchy_expressive.py:244-249;
+// class at train_hierarchy.py:23-68 / train_hierarchy_expressive.py:108-121): a [Na,32] are this rank's rows, b [Nb,32]
+// the (all-gathered) columns, row i's positive is column i + off (off = rank * Na; square single-GPU case: Nb = Na,
+// off = 0).  Logits = 1/pairwise distance of the L2-normalised rows (variant 0 gesture: 1/(D+1e-8) clamped at 1e-8;
+// 1 expressive: 1/D), cross-entropy against the positives; the N x N x 32 tensor of the reference is never built.
+// Outputs: an, bn (normalised rows), na, nb (norms), sqa, sqb (|an|^2, |bn|^2), lse [Na], G [Na,Nb] (the logits, kept for
+// backward), rowloss [Na] scratch; loss ACCUMULATED += mean over the Na local rows.
 HA2G_API int ha2g_contrastive_fwd_rect(const float* a, const float* b, float* an, float* bn, float* na, float* nb,
-                                       float* lse, float* part, float* diag, int Na, int Nb, int off, int variant,
-                                       float* loss, cudaStream_t stream) {
-    const int rows_ctas = ha2g_div_up(Na, CT);
-    int S = (148 * 4 + rows_ctas - 1) / rows_ctas;      // 4 resident CTAs per SM (launch bounds of the pair kernel)
-    const int max_s = ha2g_div_up(Nb, CT);
-    if (S > max_s) S = max_s;
-    if (S < 1) S = 1;
-    const int cols = ((Nb + S - 1) / S + CT - 1) / CT * CT;
-    l2norm_rows_kernel<<<ha2g_div_up(Na, 8), 256, 0, stream>>>(a, an, na, Na);
-    l2norm_rows_kernel<<<ha2g_div_up(Nb, 8), 256, 0, stream>>>(b, bn, nb, Nb);
-    dim3 grid(rows_ctas, ha2g_div_up(Nb, cols));
-    contrastive_pair_kernel<0><<<grid, CT, 0, stream>>>(an, bn, nullptr, part, diag, nullptr, nullptr, Na, variant, 1, cols, Nb, off);
-    contrastive_finalize_kernel<<<ha2g_div_up(Na, 256), 256, 0, stream>>>(part, diag, Na, grid.y, lse, loss);
+                                       float* sqa, float* sqb, float* lse, float* G, float* rowloss, int Na, int Nb, int off,
+                                       int variant, float* loss, cudaStream_t stream) {
+    if (Na <= 0 || Nb <= 0) return 0;
+    l2norm_rows_kernel<<<ha2g_div_up(Na, 8), 256, 0, stream>>>(a, an, na, sqa, Na);
+    l2norm_rows_kernel<<<ha2g_div_up(Nb, 8), 256, 0, stream>>>(b, bn, nb, sqb, Nb);
+    int rc = ha2g_gemm(an, bn, G, nullptr, Na, Nb, CC, CC, CC, Nb, 0, 1, 0, 0, 1, stream);   // G = an bn^T
+    if (rc != 0) return rc;
+    contrastive_rows_kernel<<<Na, 256, 0, stream>>>(G, an, bn, sqa, sqb, lse, rowloss, Nb, off, variant);
+    contrastive_mean_kernel<<<1, 1024, 0, stream>>>(rowloss, Na, loss);
     HA2G_RETURN_LAST();
 }
-// Backward of the rectangular loss: da [Na,32] and db [Nb,32] (the gradient wrt ALL gathered columns: the caller
-// reduce-scatters it to the owning ranks) = gscale * d loss / d a, b.  dan [Na,32], dbn [Nb,32]: zero-initialised scratch.
+// Backward of the rectangular loss: da [Na,32], db [Nb,32] (the gradient wrt ALL columns: under data parallelism the
+// caller reduce-scatters it to the owning ranks) = gscale * d loss / d a, b.  G holds the forward's logits and is
+// overwritten; scratch: X [Na,32], Y [Nb,32], rs [Na], cs [Nb].
 HA2G_API int ha2g_contrastive_bwd_rect(const float* an, const float* bn, const float* na, const float* nb, const float* lse,
-                                       const float* gscale, float* dan, float* dbn, float* da, float* db, int Na, int Nb,
-                                       int off, int variant, cudaStream_t stream) {
-    auto splits = [](int rows, int oth) {
-        const int rc = (rows + CT - 1) / CT;
-        int S = (148 * 4 + rc - 1) / rc;
-        const int mx = (oth + CT - 1) / CT;
-        if (S > mx) S = mx;
-        if (S < 1) S = 1;
-        return ((oth + S - 1) / S + CT - 1) / CT * CT;
-    };
-    const int cols_a = splits(Na, Nb), cols_b = splits(Nb, Na);
-    dim3 grid_a(ha2g_div_up(Na, CT), ha2g_div_up(Nb, cols_a)), grid_b(ha2g_div_up(Nb, CT), ha2g_div_up(Na, cols_b));
-    // per-column-split gradient planes in the scratch arena (dan / dbn of the signature are no longer needed)
-    (void)dan; (void)dbn;
-    const size_t pa = (size_t)grid_a.y * Na * CC, pb = (size_t)grid_b.y * Nb * CC;
-    float* plane_a = reinterpret_cast<float*>(ha2g_ws((pa + pb) * sizeof(float)));
-    if (plane_a == nullptr) return (int)cudaErrorMemoryAllocation;
-    float* plane_b = plane_a + pa;
-    contrastive_pair_kernel<1><<<grid_a, CT, 0, stream>>>(an, bn, lse, nullptr, nullptr, plane_a, gscale, Na, variant, 1, cols_a, Nb, off);
-    contrastive_pair_kernel<1><<<grid_b, CT, 0, stream>>>(bn, an, lse, nullptr, nullptr, plane_b, gscale, Nb, variant, 0, cols_b, Na, off);
-    l2norm_rows_bwd_kernel<<<ha2g_div_up(Na, 8), 256, 0, stream>>>(plane_a, (int)grid_a.y, an, na, da, Na);
-    l2norm_rows_bwd_kernel<<<ha2g_div_up(Nb, 8), 256, 0, stream>>>(plane_b, (int)grid_b.y, bn, nb, db, Nb);
+                                       const float* gscale, float* G, float* X, float* Y, float* rs, float* cs, float* da,
+                                       float* db, int Na, int Nb, int off, int variant, cudaStream_t stream) {
+    if (Na <= 0 || Nb <= 0) return 0;
+    contrastive_coef_kernel<<<Na, 256, 0, stream>>>(G, lse, gscale, rs, Na, Nb, off, variant);
+    cudaError_t ce = cudaMemsetAsync(cs, 0, sizeof(float) * (size_t)Nb, stream);
+    if (ce != cudaSuccess) return (int)ce;
+    int rc = ha2g_col_sum(G, Na, Nb, Nb, cs, stream);                                           // cs_j = sum_i C_ij
+    if (rc == 0) rc = ha2g_gemm(G, bn, X, nullptr, Na, CC, Nb, Nb, CC, CC, 0, 0, 0, 0, 1, stream);   // X = C bn
+    if (rc == 0) rc = ha2g_gemm(G, an, Y, nullptr, Nb, CC, Na, Nb, CC, CC, 1, 0, 0, 0, 1, stream);   // Y = C^T an
+    if (rc != 0) return rc;
+    contrastive_finish_kernel<<<ha2g_div_up(Na, 8), 256, 0, stream>>>(rs, an, X, na, da, Na);
+    contrastive_finish_kernel<<<ha2g_div_up(Nb, 8), 256, 0, stream>>>(cs, bn, Y, nb, db, Nb);
     HA2G_RETURN_LAST();
-}
-// Streaming SoftmaxContrastiveLoss forward (replaces criterion(text_feat, feat_*) at
-// scripts/train_eval/train_hierarchy_expressive.py:244-249; class at train_hierarchy.py:23-68): L2-normalise rows,
-// logits = 1/pairwise-distance (variant 0 gesture: 1/(D+1e-8) clamped at 1e-8; variant 1 expressive: 1/D),
-// cross-entropy against the diagonal -- tiled with an online log-sum-exp, the N x N x 32 tensor is never built.
-// a, b: [N,32].  Outputs: an, bn [N,32], na, nb [N] (normalised rows + norms), lse [N]; loss ACCUMULATED.
-// scratch: part [N * ceil(N/128) * 2] floats (upper bound), diag [N].
-HA2G_API int ha2g_contrastive_fwd(const float* a, const float* b, float* an, float* bn, float* na, float* nb, float* lse,
-                                  float* part, float* diag, int N, int variant, float* loss, cudaStream_t stream) {
-    return ha2g_contrastive_fwd_rect(a, b, an, bn, na, nb, lse, part, diag, N, N, 0, variant, loss, stream);
-}
-// Contrastive backward: da, db [N,32] = gscale * d loss/d a, d loss/d b.  dan, dbn: zero-initialised scratch [N,32].
-HA2G_API int ha2g_contrastive_bwd(const float* an, const float* bn, const float* na, const float* nb, const float* lse,
-                                  const float* gscale, float* dan, float* dbn, float* da, float* db, int N, int variant,
-                                  cudaStream_t stream) {
-    return ha2g_contrastive_bwd_rect(an, bn, na, nb, lse, gscale, dan, dbn, da, db, N, N, 0, variant, stream);
 }
 
 namespace {

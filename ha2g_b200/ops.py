@@ -120,10 +120,12 @@ _workspace = {}
 
 
 def _ensure_workspace():
-    """One torch-allocated scratch arena per device for the operand-packing passes of the tensor-core GEMMs."""
+    """One torch-allocated scratch arena per device for the operand-packing passes of the tensor-core GEMMs and the
+    partial planes of the ordered reductions (2 GB: the packed N_local x N_global coefficient matrix of the data-parallel
+    contrastive loss is the largest tenant, 0.65 GB at 8 ranks)."""
     dev = torch.cuda.current_device()
     if dev not in _workspace:
-        _workspace[dev] = torch.empty(int(os.environ.get("HA2G_WORKSPACE_MB", "512")) << 20, dtype=torch.uint8, device=f"cuda:{dev}")
+        _workspace[dev] = torch.empty(int(os.environ.get("HA2G_WORKSPACE_MB", "2048")) << 20, dtype=torch.uint8, device=f"cuda:{dev}")
         lib.ha2g_set_workspace(_workspace[dev].data_ptr(), _workspace[dev].numel())
     return _workspace[dev]
 

@@ -180,29 +180,30 @@ class _ContrastiveFn(torch.autograd.Function):
             b_all = b
         Nb = b_all.shape[0]
         an, bn = torch.empty_like(a), torch.empty_like(b_all)
-        na = torch.empty((N,), device=dev, dtype=torch.float32)
-        nb = torch.empty((Nb,), device=dev, dtype=torch.float32)
-        lse = torch.empty((N,), device=dev, dtype=torch.float32)
-        S = (Nb + 127) // 128
-        part = torch.empty((N * S * 2,), device=dev, dtype=torch.float32)
-        diag = torch.empty((N,), device=dev, dtype=torch.float32)
+        f = lambda n: torch.empty((n,), device=dev, dtype=torch.float32)
+        na, nb, sqa, sqb, lse, rowloss = f(N), f(Nb), f(N), f(Nb), f(N), f(N)
+        G = torch.empty((N, Nb), device=dev, dtype=torch.float32)   # Gram matrix -> logits -> (backward) coefficients
         loss = torch.zeros((1,), device=dev, dtype=torch.float32)
-        _call("ha2g_contrastive_fwd_rect", _p(a), _p(b_all), _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(part), _p(diag), N, Nb,
-              rank * N, variant_id, _p(loss), _st())
+        _call("ha2g_contrastive_fwd_rect", _p(a), _p(b_all), _p(an), _p(bn), _p(na), _p(nb), _p(sqa), _p(sqb), _p(lse), _p(G),
+              _p(rowloss), N, Nb, rank * N, variant_id, _p(loss), _st())
         ctx.cfg = (variant_id, world, rank)
-        ctx.save_for_backward(an, bn, na, nb, lse)
+        ctx.save_for_backward(an, bn, na, nb, lse, G)
         return loss
 
     @staticmethod
     def backward(ctx, dl):
-        an, bn, na, nb, lse = ctx.saved_tensors
+        an, bn, na, nb, lse, G = ctx.saved_tensors
         variant_id, world, rank = ctx.cfg
         N, Nb = an.shape[0], bn.shape[0]
+        dev = an.device
         dl = _c(dl)
         da, db_all = torch.empty_like(an), torch.empty_like(bn)
-        # (the launcher keeps its per-split gradient planes in the scratch arena: no caller-side scratch any more)
-        _call("ha2g_contrastive_bwd_rect", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(dl), None, None, _p(da), _p(db_all),
-              N, Nb, rank * N, variant_id, _st())
+        X, Y = torch.empty_like(an), torch.empty_like(bn)
+        rs = torch.empty((N,), device=dev, dtype=torch.float32)
+        cs = torch.empty((Nb,), device=dev, dtype=torch.float32)
+        # (G is consumed in place: the loss is differentiated once per step)
+        _call("ha2g_contrastive_bwd_rect", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(dl), _p(G), _p(X), _p(Y), _p(rs), _p(cs),
+              _p(da), _p(db_all), N, Nb, rank * N, variant_id, _st())
         if world > 1:
             import torch.distributed as dist
             db = torch.empty_like(an)

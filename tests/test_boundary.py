@@ -36,7 +36,7 @@ def test_library_exports_every_header_symbol(built):
 def test_header_cites_reference_for_core_entry_points():
     text = open(os.path.join(ROOT, "include", "ha2g_b200.h")).read()
     for sym, cite in (("ha2g_gru_layer_fwd", "hierarchy_net.py"), ("ha2g_tcn_weight_fwd", "tcn.py"),
-                      ("ha2g_conv2d_fwd", "Conv2d"), ("ha2g_contrastive_fwd", "Contrastive")):
+                      ("ha2g_conv2d_fwd", "Conv2d"), ("ha2g_contrastive_fwd_rect", "Contrastive")):
         i = text.index(f"int {sym}(")
         assert cite.lower() in text[max(0, i - 1500):i].lower(), f"{sym}: missing reference citation"
 

@@ -89,4 +89,8 @@ def test_train_iter_gan_vs_reference():
                 if "running_" in name or "num_batches" in name:
                     assert_summary_close(sd[name].float(), summ, f"gan step0 {name}", 1e-3)
                 else:
-                    assert_params_close(sd[name], summ, f"gan step0 {name}", lr, 1)
+                    # a conv bias followed directly by BatchNorm has a mathematically zero gradient: both sides hold
+                    # rounding noise there and Adam's sign-like first update moves it by +-lr arbitrarily
+                    noise_only = name in ("audio_encoder.feat_extractor.0.bias", "audio_encoder.feat_extractor.3.bias",
+                                          "audio_encoder.feat_extractor.6.bias")
+                    assert_params_close(sd[name], summ, f"gan step0 {name}", lr, 1, 1.0 if noise_only else 0.02)

@@ -466,16 +466,17 @@ def test_contrastive_rectangular_matches_square(variant):
         ar = a.detach()[r * Nl:(r + 1) * Nl].contiguous()
         ba = b.detach().contiguous()
         an, bn = torch.empty_like(ar), torch.empty_like(ba)
-        na, nb, lse, diag = (torch.empty(Nl, device=DEV), torch.empty(N, device=DEV), torch.empty(Nl, device=DEV),
-                             torch.empty(Nl, device=DEV))
-        part = torch.empty(Nl * ((N + 127) // 128) * 2, device=DEV)
+        f = lambda n: torch.empty(n, device=DEV)
+        na, nb, sqa, sqb, lse, rowloss = f(Nl), f(N), f(Nl), f(N), f(Nl), f(Nl)
+        G = torch.empty(Nl, N, device=DEV)
         loss = torch.zeros(1, device=DEV)
-        _call("ha2g_contrastive_fwd_rect", _p(ar), _p(ba), _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(part), _p(diag), Nl, N,
-              r * Nl, vid, _p(loss), _st())
+        _call("ha2g_contrastive_fwd_rect", _p(ar), _p(ba), _p(an), _p(bn), _p(na), _p(nb), _p(sqa), _p(sqb), _p(lse), _p(G),
+              _p(rowloss), Nl, N, r * Nl, vid, _p(loss), _st())
         da, db = torch.empty_like(an), torch.empty_like(bn)
+        X, Y, rs, cs = torch.empty_like(an), torch.empty_like(bn), f(Nl), f(N)
         one = torch.ones(1, device=DEV)
-        _call("ha2g_contrastive_bwd_rect", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(one), None, None, _p(da), _p(db),
-              Nl, N, r * Nl, vid, _st())
+        _call("ha2g_contrastive_bwd_rect", _p(an), _p(bn), _p(na), _p(nb), _p(lse), _p(one), _p(G), _p(X), _p(Y), _p(rs), _p(cs),
+              _p(da), _p(db), Nl, N, r * Nl, vid, _st())
         loss_sum += float(loss)
         da_parts.append(da)
         db_sum += db
