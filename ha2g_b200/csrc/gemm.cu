@@ -229,10 +229,11 @@ HA2G_API int ha2g_gemm_kseg(const float* A, const float* B, float* C, const floa
                             int kseg_stride, cudaStream_t stream) {
     const int impl = gemm_impl();
     const double flops = 2.0 * (double)M * (double)N * (double)K;
-    // Tensor-core path (bf16 hi + lo operands: 2^-17 operand representation, ~2e-6 output error) for problems that fill at
-    // least two 128-row tiles and amortise the packing pass; small problems stay on the exact fp32 SIMT kernel (they gain
-    // nothing from tcgen05, and the B = 2..5 parity fixtures then see fp32 arithmetic end to end).
-    if (impl == 3 || (impl == 1 && flops >= 6.0e7 && K >= 32 && M >= 256))
+    // Tensor-core path (bf16 hi + lo operands: 2^-18 operand representation, ~2e-6 output error) for problems that amortise
+    // the packing pass: at least two 128-row tiles of output rows, or a long reduction (the weight-gradient GEMMs: few output
+    // rows, K = batch x time).  Small problems stay on the exact fp32 SIMT kernel (they gain nothing from tcgen05, and the
+    // B = 2..5 parity fixtures then see fp32 arithmetic end to end).
+    if (impl == 3 || (impl == 1 && flops >= 6.0e7 && K >= 32 && (M >= 256 || K >= 1024)))
         return ha2g_gemm_tc2(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, act, accumulate, split_k, kseg_len,
                              kseg_stride, gemm_terms(), stream);
     return ha2g_gemm_f32_kseg(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, act, accumulate, split_k, kseg_len,

@@ -113,6 +113,54 @@ __global__ void pack_bf16x2_kernel(const float* __restrict__ src, int ld, int ro
     }
 }
 
+// Both operands of one GEMM in a single launch: CTAs [0, ctas_a) pack A, the rest pack B (same per-element code as
+// pack_bf16x2_kernel; halves the launch count of the packing passes, ~950 -> ~480 per training step).
+struct PackJob {
+    const float* src; int ld, rows, K, kcontig, kseg_len, kseg_stride; uint4* hi; uint4* lo; int rows_p, chunks_p;
+};
+__device__ __forceinline__ void pack_elems(const PackJob& j, int64_t first, int64_t stride) {
+    const int64_t total = (int64_t)j.rows_p * j.chunks_p;
+    for (int64_t e = first; e < total; e += stride) {
+        const int row = (int)(e % j.rows_p);
+        const int c = (int)(e / j.rows_p);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (row < j.rows) {
+            const int k0 = c * 8;
+            if (j.kcontig) {
+                const float* p = j.src + (size_t)row * j.ld + k0;
+                if (k0 + 7 < j.K && (j.ld & 3) == 0 && (((uintptr_t)j.src & 15) == 0)) {
+                    const float4 a = *reinterpret_cast<const float4*>(p);
+                    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (k0 + i < j.K) v[i] = p[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = k0 + i;
+                    if (k < j.K) {
+                        const size_t prow = j.kseg_len > 0 ? (size_t)(k / j.kseg_len) * j.kseg_stride + (k % j.kseg_len) : (size_t)k;
+                        v[i] = j.src[prow * j.ld + row];
+                    }
+                }
+            }
+        }
+        uint4 h, l;
+        split2p(v[0], v[1], h.x, l.x); split2p(v[2], v[3], h.y, l.y);
+        split2p(v[4], v[5], h.z, l.z); split2p(v[6], v[7], h.w, l.w);
+        j.hi[e] = h;
+        j.lo[e] = l;
+    }
+}
+__global__ void pack_pair_kernel(PackJob a, PackJob b, int ctas_a) {
+    if ((int)blockIdx.x < ctas_a) pack_elems(a, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)ctas_a * blockDim.x);
+    else pack_elems(b, (blockIdx.x - ctas_a) * (int64_t)blockDim.x + threadIdx.x, (int64_t)(gridDim.x - ctas_a) * blockDim.x);
+}
+
 template <int BN>
 struct PSmem {
     static constexpr int A_BYTES = PBM * PBK * 2;
@@ -423,8 +471,15 @@ HA2G_API int ha2g_gemm_tc2(const float* A, const float* B, float* C, const float
             if (s > 1) split_k = s;   // the ordered reduction overwrites C when accumulate == 0
         }
     }
-    int rc = ha2g_pack_bf16x2(A, lda, M, K, transA ? 0 : 1, kseg_len, kseg_stride, ah, al, stream);
-    if (rc == 0) rc = ha2g_pack_bf16x2(B, ldb, N, K, transB ? 1 : 0, kseg_len, kseg_stride, bh, bl, stream);
+    int rc = 0;
+    {   // both operands in one launch
+        PackJob ja{A, lda, M, K, transA ? 0 : 1, kseg_len, kseg_stride, reinterpret_cast<uint4*>(ah), reinterpret_cast<uint4*>(al), rpa, cp};
+        PackJob jb{B, ldb, N, K, transB ? 1 : 0, kseg_len, kseg_stride, reinterpret_cast<uint4*>(bh), reinterpret_cast<uint4*>(bl), rpb, cp};
+        const int ca = ha2g_ew_grid((int64_t)rpa * cp, 256, 2), cb = ha2g_ew_grid((int64_t)rpb * cp, 256, 2);
+        pack_pair_kernel<<<ca + cb, 256, 0, stream>>>(ja, jb, ca);
+        cudaError_t pe = cudaPeekAtLastError();
+        if (pe != cudaSuccess) rc = (int)pe;
+    }
     if (rc == 0) rc = ha2g_gemm_packed(ah, al, rpa, bh, bl, rpb, C, bias, M, N, cp, ldc, act, accumulate, split_k, terms, stream);
     return rc;
 }
