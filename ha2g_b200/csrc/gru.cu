@@ -260,8 +260,13 @@ HA2G_API int ha2g_gru_layer_bwd(const float* dy, int dy_ld, int dy_dir_stride, c
     }
     // dx = dgi_f W_ih_f + dgi_r W_ih_r            ([MT,3H] x [3H,I])
     if (dx != nullptr) {
-        HA2G_CHECK(ha2g_gemm(dgi, w_ih_f, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 0, 1, stream));
-        HA2G_CHECK(ha2g_gemm(dgi + 3 * H, w_ih_r, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 1, 1, stream));
+        if (w_ih_r == w_ih_f + (size_t)3 * H * I) {
+            // both directions' input weights are adjacent (one [6H, I] matrix): ONE GEMM over K = 6H, dgi packed once
+            HA2G_CHECK(ha2g_gemm(dgi, w_ih_f, dx, nullptr, MT, I, 6 * H, 6 * H, I, I, 0, 0, 0, 0, 1, stream));
+        } else {
+            HA2G_CHECK(ha2g_gemm(dgi, w_ih_f, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 0, 1, stream));
+            HA2G_CHECK(ha2g_gemm(dgi + 3 * H, w_ih_r, dx, nullptr, MT, I, 3 * H, 6 * H, I, I, 0, 0, 0, 1, 1, stream));
+        }
     }
     HA2G_RETURN_LAST();
 }

@@ -507,9 +507,15 @@ class _BiGRUFn(torch.autograd.Function):
         saved: List[torch.Tensor] = []
         masks = []
         cur = x
+        wcats = []
         for l in range(L):
             w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = weights[8 * l:8 * l + 8]
             I = cur.shape[2]
+            # both directions' input weights / biases stacked ([6H, I] / [6H]): the launcher then runs ONE projection GEMM
+            # with N = 6H (x packed once) and, in backward, ONE dx GEMM over K = 6H
+            wcat, bcat = torch.cat([w_ih, w_ih_r], 0), torch.cat([b_ih, b_ih_r], 0)
+            wcats.append(wcat)
+            w_ih, w_ih_r, b_ih, b_ih_r = wcat[:3 * H], wcat[3 * H:], bcat[:3 * H], bcat[3 * H:]
             gi = torch.empty((MF, T, 6 * H), device=x.device, dtype=torch.float32)
             yf, y = _alloc((M, T, 2 * H), x.device)
             # the gates are saved for the head rows only: the companions are never differentiated
@@ -541,6 +547,7 @@ class _BiGRUFn(torch.autograd.Function):
         ctx.cfg = (H, L, p, sum_dirs, M, T)
         ctx.masks = masks
         ctx.nw = len(weights)
+        ctx.wcats = wcats if need_grad else None
         ctx.save_for_backward(*saved, *weights)
         return out
 
@@ -561,6 +568,7 @@ class _BiGRUFn(torch.autograd.Function):
         for l in range(L - 1, -1, -1):
             xin, y, gates = saved[3 * l:3 * l + 3]
             w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = weights[8 * l:8 * l + 8]
+            w_ih, w_ih_r = ctx.wcats[l][:3 * H], ctx.wcats[l][3 * H:]     # the stacked copy made in forward (one dx GEMM)
             I = xin.shape[2]
             # both directions' gradients of one kind live in ONE buffer: the launcher then needs a single GEMM for
             # dW_ih (dgi^T x over all 6H gate columns) and a single column sum per bias pair, and 4 zero-fills, not 8
