@@ -1,28 +1,34 @@
 // Persistent cluster GRU recurrence, second generation (forward) -- the fused GRU kernel of the step.
 //
-// Decomposition: an 8-CTA cluster per (direction, NB-row batch chunk), NB = 16 / 32 / 48 chosen from the batch so that the
-// 16 resident clusters cover it in one wave (M <= 128 / <= 256 / larger: the 3B-row cascade of the training step runs at
-// NB = 48); CTA `rank` owns HSP = 40 hidden units = 3*HSP gate rows (r | z | n, zero-padded to M = 128) of W_hh for all T
-// steps, and every step computes
-//     gates^T[128 x NB] = W_slice[128 x K] * h_{t-1}^T[K x NB]          (K = 8*HSP = 320, bf16x3 split, fp32 accumulate)
-// on tcgen05: the same 60 tcgen05.mma per step carry NB columns, the fixed per-step latency (mbarrier wake-ups, TMEM
-// round trip, DSMEM flight) is amortised over NB rows, and with NB > 16 eight epilogue warps (two per TMEM lane quarter,
-// each taking half of the columns) keep the gate math at one 8-unit item per thread.
-// History, each item taken from the phase timing of the first kernel (tools/time_gru_tc.py:
-// 10 600 cycles per step = MMA issue 4 170 + gate math/stores 3 230 + DSMEM push 1 950 + cluster barrier 910):
+// Decomposition: an 8-CTA cluster per (direction, NB-row batch chunk).  A B200 keeps 15 such clusters resident (a cluster
+// lives inside one GPC; measured with cudaOccupancyMaxActiveClusters and tools/gru_waves.py), i.e. 7 per direction: NB is
+// the smallest of 16 / 20 / 32 / 48 / 56 / 64 whose chunks fit that one wave (the 3B = 384-row cascade of the training step
+// runs at NB = 56, a 128-row batch at NB = 20).  Until round 2 the launcher assumed 16 resident clusters: the 16th waited
+// for a whole sequence and every recurrence of the step ran at twice its one-wave time.
+// CTA `rank` owns HSP = 40 hidden units = 3*HSP gate rows (r | z | n, zero-padded to M = 128) of W_hh for all T steps, and
+// every step computes
+//     gates^T[128 x NN] = W_slice[128 x K] * h_{t-1}^T[K x NN]          (K = 8*HSP = 320, bf16x3 split, fp32 accumulate)
+// on tcgen05 (NN = NB rounded up to the UMMA N granularity of 16; accumulator columns >= NB are never read): the same 60
+// tcgen05.mma per step carry NB columns, the fixed per-step latency (mbarrier wake-ups, TMEM round trip, DSMEM flight)
+// is amortised over NB rows, and 4 / 8 / 10 epilogue warps keep the gate math at one 8-unit item per thread.
+// History, each item taken from phase timings (tools/time_gru_tc.py; first kernel: 10 600 cycles per step =
+// MMA issue 4 170 + gate math/stores 3 230 + DSMEM push 1 950 + cluster barrier 910):
 //   * W_slice lives in TENSOR MEMORY (tcgen05.st once per layer, 320 columns: hi | lo) and is the MMA's A operand
-//     straight from TMEM.  With A in shared memory every one of the 60 MMAs of a step re-read 4 KB of weights through
-//     the 128 B/clk shared-memory port (240 KB per step = the 4 170 cycles); now a step reads only h (30 KB).
-//   * h_t travels by bulk asynchronous copies (cp.async.bulk shared::cta -> shared::cluster, 2.5 KB per destination,
-//     8 per CTA per step, issued by 8 lanes) that complete_tx on the DESTINATION's mbarrier.  The MMA thread of each CTA
-//     waits on its own mbarrier for 8 x 2.5 KB: no generic-proxy remote stores, no proxy fence over remote traffic, no
-//     cluster barrier inside the time loop.  Double-buffered h and staging make the reuse distances safe (see below).
+//     straight from TMEM: 57 dependent MMAs of N = 48 take 1 470 cycles (tools/ubench/mma_chain.cu: 26 cycles each,
+//     the 128*N/256 floor; with A in shared memory 46).
+//   * h_t travels by bulk asynchronous copies (cp.async.bulk shared::cta -> shared::cluster): every item thread writes
+//     its packed chunk into the CTA's own slice of the next h buffer, one lane hands that slice to the copy engine once
+//     per peer, and each copy completes its bytes on the DESTINATION's mbarrier.  The MMA thread waits on its own
+//     mbarrier for the 7 peer slices plus a local arrival for the own one: no cluster barrier inside the time loop, and
+//     no remote traffic through the load/store unit (an intermediate version pushed with st.async from registers: fine
+//     at NB = 16, but at NB = 48 the 61 KB per step occupied the LSU for ~3 000 cycles per step).
 //   * y / saved-gate stores to global memory are issued AFTER the h push, off the recurrence's critical path.
-// h buffer layout (per buffer): [K/8 chunks][hi | lo][16 rows][8 bf16] = UMMA canonical K-major no-swizzle core matrices
-// with LBO = 512 B; a rank's slice (its 5 chunks, hi and lo) is one contiguous 2 560 B range = one bulk copy.
+// h buffer layout (per buffer): [K/8 chunks][hi | lo][NR rows][8 bf16] = UMMA canonical K-major no-swizzle core matrices
+// (NR = NB rounded up to 8) with LBO = 2*NR*16 B; a rank's slice (its 5 chunks, hi and lo) is one contiguous range = one bulk copy.
 // Reuse distances: step s reads buffer s&1 and its epilogue fills buffer (s+1)&1 of all CTAs.  A peer can only be
 // writing h_{s+1} into my buffer s&1 after it has received MY h_s, which I send after my step-s MMA has completed --
-// so no copy ever lands in a buffer an MMA is still reading; the same argument two steps apart covers the staging pair.
+// so no copy ever lands in a buffer an MMA is still reading; and my own slice of buffer (s+1)&1, the source of the
+// copies of step s, is next written at step s+2, after every peer's h_{s+1} (hence their receipt of my h_s) has arrived.
 // Replaces nn.GRU's recurrence at scripts/model/hierarchy_net.py:144 (H = 300) and :232 (H = 64).
 #include "common.cuh"
 #include <cooperative_groups.h>
@@ -37,8 +43,13 @@ constexpr int CL = 8;          // CTAs per cluster
 constexpr int TM = 128;        // UMMA M (gate rows incl. padding)
 constexpr int TMEM_COLS = 512; // D at columns [0,NB), W_slice hi at [64, 64+K/2), lo right after
 constexpr int A_COL = 64;
-// NB = batch rows per cluster task (= UMMA N); epilogue warps: 4 at NB = 16, 8 above (warp 0 issues the MMAs)
-__host__ __device__ constexpr int epi_warps(int NB) { return NB == 16 ? 4 : 8; }
+// NB = batch rows per cluster task, NN = UMMA N (>= NB, multiple of 16; accumulator columns >= NB are never read).
+// Epilogue warps (warp 0 issues the MMAs): one (8-unit chunk, batch row) gate item per thread -> 4 / 8 / 10 warps.
+__host__ __device__ constexpr int epi_warps(int NB) { return NB <= 24 ? 4 : (NB <= 48 ? 8 : 10); }
+__host__ __device__ constexpr int mma_n(int NB) { return (NB + 15) / 16 * 16; }
+// accumulator columns per epilogue warp: the NB columns are split over the 1 - 3 warps that share a TMEM lane quarter, in
+// multiples of 8; this is the largest share (quarters served by 2 of the 10 warps)
+__host__ __device__ constexpr int cols_per_warp(int NB) { return ((NB + epi_warps(NB) / 4 - 1) / (epi_warps(NB) / 4) + 7) / 8 * 8; }
 __host__ __device__ constexpr int block_threads(int NB) { return 32 + 32 * epi_warps(NB); }
 constexpr size_t MIN_SMEM = 120 * 1024;  // > half of the SM's shared memory: one CTA per SM, so the 512-column TMEM
                                          // allocation can never wait on a co-resident CTA of the same cluster
@@ -51,6 +62,7 @@ struct Tc2Params {
     float* gates;          // [M,T,2,4H] or nullptr
     int M, T, H, HSP, n_chunks;
     int M_gates;           // gates are stored for batch rows < M_gates only (the rows whose BPTT will run)
+    int xflags;            // timing experiments only (tools/time_gru_tc.py): 1 = no gi loads, 2 = no global stores, 4 = no staging
     long long* dbg;        // optional [T+1][8] clock64 samples of cluster 0 / rank 0 (phase timing), nullptr otherwise
 };
 
@@ -71,22 +83,11 @@ __device__ __forceinline__ void mbw(uint64_t* bar, uint32_t parity) {
         if (!done && clock64() - t0 > 4000000000LL) __trap();
     }
 }
-// wait with acquire at CLUSTER scope: the bytes were written by st.async from the other CTAs of the cluster
-__device__ __forceinline__ void mbw_cluster(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = su32(bar);
-    uint32_t done = 0;
-    long long t0 = clock64();
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (!done && clock64() - t0 > 4000000000LL) __trap();
-    }
-}
 __device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(su32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(su32(bar)) : "memory");
 }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -96,11 +97,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
-}
-// 16 bytes to another CTA's shared memory; completes 16 bytes of the transaction count of that CTA's mbarrier
-__device__ __forceinline__ void st_async16(uint32_t dst_cluster, const uint4& v, uint32_t mbar_cluster) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                 ::"r"(dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster) : "memory");
 }
 __device__ __forceinline__ uint64_t mkd(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -129,20 +125,34 @@ __device__ __forceinline__ void split2g(float a, float b, uint32_t& hi, uint32_t
 // fp32 staging of the CTA's W_hh rows (consumed into tensor memory before the first task starts)
 struct Tc2Layout {
     int kc;  // K chunks = CL * HSP / 8
-    size_t b_bytes, slice_bytes, off_h, off_g, off_hown, off_out, off_bar, off_w, total;
-    int orow;   // floats per (array, batch row) line of the output staging (HSP + 4: conflict-free 128-bit stores)
+    size_t b_bytes, slice_bytes, off_h, off_g, off_hown, off_out, off_bias, off_bar, off_w, total;
+    int orow;   // floats per (array, batch row) line of the output staging and of hown (HSP + 4: 128-bit accesses)
+    int grow;   // floats per batch row of the transposed accumulator (3*HSP + 4)
     __host__ __device__ Tc2Layout(int HSP, int H, int NB) {
+        const int NR = (NB + 7) / 8 * 8;   // rows per (chunk, hi | lo) block of the B operand: whole 8-row core matrices
         kc = CL * HSP / 8;
-        b_bytes = (size_t)kc * 2 * NB * 16;
-        slice_bytes = (size_t)(HSP / 8) * 2 * NB * 16;
+        b_bytes = (size_t)kc * 2 * NR * 16;
+        slice_bytes = (size_t)(HSP / 8) * 2 * NR * 16;
         off_bar = 0;
         off_h = 128;
         off_w = 128;
         off_g = off_h + 2 * b_bytes;
-        off_hown = off_g + (size_t)TM * (NB + 1) * 4;
-        off_out = (off_hown + (size_t)HSP * NB * 4 + 15) / 16 * 16;
         orow = HSP + 4;
-        const size_t loop_end = off_out + (size_t)5 * NB * orow * 4;   // y | r | z | n | hn lines of one step
+        grow = 3 * HSP + 4;
+        const size_t gsz = (size_t)NB * grow * 4, hsz = (size_t)NB * orow * 4;
+        size_t loop_end;
+        if (NB <= 48) {
+            off_hown = off_g + gsz;
+            off_out = off_hown + hsz;
+            loop_end = off_out + (size_t)5 * NB * orow * 4;   // y | r | z | n | hn lines of one step
+        } else {   // NB = 56 / 64: the output staging reuses the accumulator transpose buffer (two extra barriers per step)
+            off_out = off_g;
+            const size_t osz = (size_t)5 * NB * orow * 4;
+            off_hown = off_g + (gsz > osz ? gsz : osz);
+            loop_end = off_hown + hsz;
+        }
+        off_bias = loop_end;                                           // hidden-side biases of the CTA's units: [3][HSP]
+        loop_end += (size_t)3 * HSP * 4;
         const size_t w_end = off_w + (size_t)3 * HSP * H * 4;          // fp32 W_hh rows of this CTA, bulk-copied once
         total = loop_end > w_end ? loop_end : w_end;
         total = (total + 127) / 128 * 128;
@@ -155,7 +165,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     constexpr int NEW = epi_warps(NB);          // epilogue warps
     constexpr int TNT = block_threads(NB);
     constexpr int NET = 32 * NEW;               // epilogue threads
-    constexpr int CPW = NB / (NEW / 4);         // accumulator columns handled per epilogue warp
+    constexpr int NN = mma_n(NB);               // UMMA N (multiple of 16)
+    // rows per (chunk, hi | lo) block of the B operand.  When NR < NN (NB = 20, 56) the MMA's last 8-row group reads the
+    // first rows of the NEXT block: finite or not, they only reach accumulator columns >= NR, which nobody reads.
+    constexpr int NR = (NB + 7) / 8 * 8;
+    constexpr int CPW = cols_per_warp(NB);      // most accumulator columns any epilogue warp handles
+    constexpr bool ALIAS = NB > 48;             // output staging aliases the transpose buffer
     extern __shared__ __align__(128) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -165,9 +180,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     const Tc2Layout L(HSP, H, NB);
     const int KC = L.kc;                 // K chunks (K = 8*KC)
     const int CPC = HSP / 8;             // chunks owned per CTA
-    unsigned char* hbuf = smem + L.off_h;               // [2][KC][2][NB][16 B]
-    float* G = reinterpret_cast<float*>(smem + L.off_g);         // [TM][NB+1]
-    float* hown = reinterpret_cast<float*>(smem + L.off_hown);   // [HSP][NB]
+    unsigned char* hbuf = smem + L.off_h;               // [2][KC][2][NR][16 B]
+    float* G = reinterpret_cast<float*>(smem + L.off_g);         // [NB][grow]: W_hh h of batch row b, gate rows r | z | n
+    float* hown = reinterpret_cast<float*>(smem + L.off_hown);   // [NB][orow]: fp32 master copy of the CTA's units of h
     float* outst = reinterpret_cast<float*>(smem + L.off_out);   // [5][NB][orow]
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* bar_full = bar_mma + 1;                   // [2]: h buffer b complete (8 x slice_bytes landed)
@@ -186,14 +201,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     float* __restrict__ g_gates = p.gates;
     long long* g_dbg = p.dbg;
     const int M_gates = p.M_gates;
-    const uint32_t tx_bytes = (uint32_t)(CL * L.slice_bytes);
+    const int xflags = p.xflags;
+    const uint32_t tx_bytes = (uint32_t)((CL - 1) * L.slice_bytes);   // the 7 peer slices; the own one is a plain arrival
 
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
     if (dbg_on && tid == 0) p.dbg[p.T * 8 + 0] = clock64();
     if (tid == 0) {
         mbi(bar_mma, 1);
-        mbi(bar_full + 0, 1);
-        mbi(bar_full + 1, 1);
+        mbi(bar_full + 0, 2);   // arrive.expect_tx of the MMA thread + the arrival that signs off the CTA's own slice
+        mbi(bar_full + 1, 2);
         mbi(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -207,16 +223,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t tmem_d = tmem_base;
     const uint32_t tmem_ahi = tmem_base + A_COL, tmem_alo = tmem_base + A_COL + (uint32_t)KC * 4;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
     // epilogue roles: warp -> TMEM lane quarter (warp & 3) and, with 8 warps, column half (warp - 1) / 4;
     // gate item = (chunk cc of the CTA, batch row b)
     const int et = tid - 32;                        // 0..NET-1 for epilogue threads
     const bool is_epi = warp >= 1;
     const int q = warp & 3;
-    const int col0 = is_epi ? ((warp - 1) >> 2) * CPW : 0;   // first accumulator column of this warp
-    const int cc = is_epi ? et / NB : 0, bb = is_epi ? et % NB : 0;
-    const bool has_item = is_epi && cc < CPC;
+    // accumulator columns of this warp: the warps w = q, q+4, q+8 <= NEW share lane quarter q and split the NB columns
+    const int nwq = q == 0 ? NEW / 4 : (NEW - q) / 4 + 1;
+    const int cpw = ((NB + nwq - 1) / nwq + 7) / 8 * 8;
+    const int col0 = is_epi ? ((warp - 1) >> 2) * cpw : 0;   // first accumulator column of this warp
+    // item -> thread: the chunk index runs fastest, so that a warp's 32 items cover ~6 batch rows x the CTA's 160
+    // contiguous bytes per row of every global tensor (lanes across batch rows made every 128-bit load / store touch 32
+    // different lines and kept the load/store unit busy for ~1 500 cycles per step)
+    const int cc = is_epi ? et % CPC : 0, bb = is_epi ? et / CPC : 0;
+    const bool has_item = is_epi && bb < NB;
 
     // ---- one-time: this CTA's W_hh rows (r | z | n of units j0..j0+HSP) as bf16 hi/lo into tensor memory -------------
     // global -> shared: one bulk copy per gate row (H*4 contiguous bytes), all in flight at once
@@ -274,19 +296,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (dbg_on && tid == 0) g_dbg[p.T * 8 + 2] = clock64();
-    // B descriptors: chunk stride (K direction, LBO) = 2*NB*16 (hi and lo of a chunk are adjacent), 8-row groups 128 B apart
-    const uint32_t lbo = 2 * NB * 16;
-    const uint64_t dbh0 = mkd(su32(hbuf), lbo, 128), dbl0 = mkd(su32(hbuf + NB * 16), lbo, 128);
-    const uint64_t dbh1 = mkd(su32(hbuf + L.b_bytes), lbo, 128), dbl1 = mkd(su32(hbuf + L.b_bytes + NB * 16), lbo, 128);
+    // B descriptors: chunk stride (K direction, LBO) = 2*NR*16 (hi and lo of a chunk are adjacent), 8-row groups 128 B apart
+    const uint32_t lbo = 2 * NR * 16;
+    const uint64_t dbh0 = mkd(su32(hbuf), lbo, 128), dbl0 = mkd(su32(hbuf + NR * 16), lbo, 128);
+    const uint64_t dbh1 = mkd(su32(hbuf + L.b_bytes), lbo, 128), dbl1 = mkd(su32(hbuf + L.b_bytes + NR * 16), lbo, 128);
     const uint64_t b_step = (uint64_t)((2 * lbo) >> 4);   // one K = 16 step = two chunks
-    // hidden-side biases of this thread's 8 units (constant over the sequence)
-    float bhr[8], bhz[8], bhn[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int j = j0 + cc * 8 + i;
-        const bool okj = has_item && j < H;
-        bhr[i] = okj ? b_hh[j] : 0.f; bhz[i] = okj ? b_hh[H + j] : 0.f; bhn[i] = okj ? b_hh[2 * H + j] : 0.f;
+    // hidden-side biases of the CTA's units (constant over the sequence) in shared memory, [gate][HSP]: re-read as
+    // broadcast 128-bit words every step rather than held in 24 registers per thread (the W_hh staging is dead by now)
+    float* bsm = reinterpret_cast<float*>(smem + L.off_bias);
+    for (int e = tid; e < 3 * HSP; e += TNT) {
+        const int g = e / HSP, j = j0 + e % HSP;
+        bsm[e] = j < H ? b_hh[g * H + j] : 0.f;
     }
+    // (made visible to the epilogue warps by the cluster.sync() that opens the first task)
     // copy-out roles (fixed per thread; NB * HSP/4 <= 2 * NET float4 per line group)
     int co_n = 0, co_rb[2] = {0, 0}, co_f4[2] = {0, 0};
     if (is_epi) {
@@ -301,9 +323,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
 
     for (int task = cluster_id >> 1; task < p.n_chunks; task += n_clusters >> 1) {
         const int m0 = task * NB;
-        // h_{-1} = 0: buffer 0 (hi and lo) and the fp32 master copy
-        for (int e = tid; e < KC * 2 * NB; e += TNT) reinterpret_cast<uint4*>(hbuf)[e] = make_uint4(0, 0, 0, 0);
-        for (int e = tid; e < HSP * NB; e += TNT) hown[e] = 0.f;
+        // h_{-1} = 0: buffer 0 (hi and lo) and the fp32 master copy; buffer 1 too, for the rows NB..NR-1 nobody writes
+        for (int e = tid; e < 2 * KC * 2 * NR; e += TNT) reinterpret_cast<uint4*>(hbuf)[e] = make_uint4(0, 0, 0, 0);
+        for (int e = tid; e < NB * L.orow; e += TNT) hown[e] = 0.f;
         asm volatile("fence.proxy.async;" ::: "memory");
         if (tid == 0) {   // h_0 lands in buffer 1 (consumed by step 1), h_1 in buffer 0 (consumed by step 2)
             if (T >= 2) mb_expect_tx(bar_full + 1, tx_bytes);
@@ -320,7 +342,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
             for (int i = 0; i < 8; ++i) gir[i] = giz[i] = gin[i] = 0.f;
             const int b = m0 + bb;
             const int jbase = j0 + cc * 8;
-            if (!(has_item && b < M) || s_next >= T) return;
+            if (!(has_item && b < M) || s_next >= T || (xflags & 1)) return;
             const int tn = dir == 0 ? s_next : T - 1 - s_next;
             const float* g = g_gi + (((size_t)b * T + tn) * 2 + dir) * 3 * H;
             if (jbase + 7 < H) {   // whole 8-unit chunk valid -> 128-bit accesses (rows are 16-byte aligned)
@@ -346,14 +368,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
             if (warp == 0) {   // whole warp, converged; one elected lane issues
                 if (dbg_on && lane == 0) g_dbg[s * 8 + 7] = clock64();
                 // (measured: splitting the wait into per-rank-pair barriers so that the MMAs start under the arrival of the
-                // remaining slices LOST 4-14 % -- the slices land together, and every extra acquire wait costs a CCTL.IVALL)
+                // remaining slices LOST 4-14 % -- the slices land together)
                 if (s > 0) {
-                    mbw_cluster(bar_full + cur, cur ? full_ph1 : full_ph0);
+                    mbw(bar_full + cur, cur ? full_ph1 : full_ph0);
                     if (cur) full_ph1 ^= 1; else full_ph0 ^= 1;
                 }
                 if (dbg_on && lane == 0) g_dbg[s * 8 + 0] = clock64();
-                // st.async data (generic proxy of the peers) -> visible to the tensor core's async proxy
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // (the peers' slices were written by the bulk-copy engine, the own one behind a proxy fence: all visible to
+                // the tensor core's async proxy once the barrier has completed)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (ha2g_elect_one()) {
                     if (s > 0 && s + 2 <= T - 1) mb_expect_tx(bar_full + cur, tx_bytes);   // h_{s+1} will land here
@@ -387,15 +409,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                     const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
 #pragma unroll
                     for (int c8 = 0; c8 < CPW / 8; ++c8)
+                        if (c8 * 8 < cpw && col0 + c8 * 8 < NB)
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                             : "=r"(r[c8 * 8 + 0]), "=r"(r[c8 * 8 + 1]), "=r"(r[c8 * 8 + 2]), "=r"(r[c8 * 8 + 3]),
                               "=r"(r[c8 * 8 + 4]), "=r"(r[c8 * 8 + 5]), "=r"(r[c8 * 8 + 6]), "=r"(r[c8 * 8 + 7])
                             : "r"(taddr + (uint32_t)(c8 * 8)));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float* grow = G + (size_t)(q * 32 + lane) * (NB + 1) + col0;
+                    // transposed: a warp writes 32 consecutive gate rows of one batch row per instruction (conflict-free),
+                    // and the gate math below reads its 8 units of a gate as two 128-bit words
+                    const int grow_i = q * 32 + lane;
+                    if (grow_i < 3 * HSP) {
+                        float* gcol = G + (size_t)col0 * L.grow + grow_i;
 #pragma unroll
-                    for (int i = 0; i < CPW; ++i) grow[i] = __uint_as_float(r[i]);
+                        for (int i = 0; i < CPW; ++i)
+                            if (i < cpw && col0 + i < NB) gcol[(size_t)i * L.grow] = __uint_as_float(r[i]);
+                    }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");  // the epilogue warps
@@ -406,13 +435,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                 if (has_item) {
                     // branch-free over the 8 units (a per-unit `if` serialises the eight ~150-cycle dependency chains)
                     float hr8[8], hz8[8], hn8[8], hp8[8];
+                    {
+                        const float* gb = G + (size_t)bb * L.grow + cc * 8;
+                        const float4 r0 = *reinterpret_cast<const float4*>(gb), r1 = *reinterpret_cast<const float4*>(gb + 4);
+                        const float4 z0 = *reinterpret_cast<const float4*>(gb + HSP), z1 = *reinterpret_cast<const float4*>(gb + HSP + 4);
+                        const float4 n0 = *reinterpret_cast<const float4*>(gb + 2 * HSP), n1 = *reinterpret_cast<const float4*>(gb + 2 * HSP + 4);
+                        const float* hb = hown + (size_t)bb * L.orow + cc * 8;
+                        const float4 p0 = *reinterpret_cast<const float4*>(hb), p1 = *reinterpret_cast<const float4*>(hb + 4);
+                        hr8[0] = r0.x; hr8[1] = r0.y; hr8[2] = r0.z; hr8[3] = r0.w; hr8[4] = r1.x; hr8[5] = r1.y; hr8[6] = r1.z; hr8[7] = r1.w;
+                        hz8[0] = z0.x; hz8[1] = z0.y; hz8[2] = z0.z; hz8[3] = z0.w; hz8[4] = z1.x; hz8[5] = z1.y; hz8[6] = z1.z; hz8[7] = z1.w;
+                        hn8[0] = n0.x; hn8[1] = n0.y; hn8[2] = n0.z; hn8[3] = n0.w; hn8[4] = n1.x; hn8[5] = n1.y; hn8[6] = n1.z; hn8[7] = n1.w;
+                        hp8[0] = p0.x; hp8[1] = p0.y; hp8[2] = p0.z; hp8[3] = p0.w; hp8[4] = p1.x; hp8[5] = p1.y; hp8[6] = p1.z; hp8[7] = p1.w;
+                        const float* bb8 = bsm + cc * 8;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int u = cc * 8 + i;
-                        hr8[i] = G[(size_t)u * (NB + 1) + bb] + bhr[i];
-                        hz8[i] = G[(size_t)(HSP + u) * (NB + 1) + bb] + bhz[i];
-                        hn8[i] = G[(size_t)(2 * HSP + u) * (NB + 1) + bb] + bhn[i];
-                        hp8[i] = hown[u * NB + bb];
+                        for (int i = 0; i < 8; ++i) { hr8[i] += bb8[i]; hz8[i] += bb8[HSP + i]; hn8[i] += bb8[2 * HSP + i]; }
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -425,29 +461,44 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                         hnew[i] = ok ? (1.f - z) * n + z * hp8[i] : 0.f;
                         sr[i] = r; sz[i] = z; sn[i] = n; shn[i] = hn8[i];
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) hown[(cc * 8 + i) * NB + bb] = hnew[i];
+                    {
+                        float* hb = hown + (size_t)bb * L.orow + cc * 8;
+                        reinterpret_cast<float4*>(hb)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+                        reinterpret_cast<float4*>(hb)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
+                    }
                 }
                 if (dbg_on && tid == 32) g_dbg[s * 8 + 4] = clock64();
                 if (s < T - 1) {
-                    // ---- push h_t: every item thread sends its packed 8-unit chunk (hi and lo, 16 bytes each) straight from
-                    // registers to all 8 CTAs with st.async, which also signs the bytes off on the DESTINATION's mbarrier:
-                    // no staging buffer, no proxy fence, no barrier, and one DSMEM hop of latency instead of a trip
-                    // through the bulk-copy engine (measured: ~1.1 us -> see tools/time_gru_tc.py)
+                    // ---- push h_t: every item thread writes its packed 8-unit chunk (hi and lo, 16 bytes each) into the CTA's
+                    // OWN slice of the next h buffer; one lane then hands the slice to the bulk-copy engine, once per peer,
+                    // each copy signing its bytes off on the DESTINATION's mbarrier, and signs the own slice off locally.
+                    // (First version: 16 st.async per thread straight from registers -- lowest latency, but the 61 KB per
+                    // step left the SM through the load/store unit at ~21 B/clk and kept it busy for ~3 000 cycles per step,
+                    // stalling the y / gate stores and the next step's loads behind it; the copy engine moves the same
+                    // bytes without occupying the LSU.)
+                    unsigned char* nxt = hbuf + (size_t)(cur ^ 1) * L.b_bytes;
                     if (has_item) {
                         uint4 h4, l4;
                         split2g(hnew[0], hnew[1], h4.x, l4.x); split2g(hnew[2], hnew[3], h4.y, l4.y);
                         split2g(hnew[4], hnew[5], h4.z, l4.z); split2g(hnew[6], hnew[7], h4.w, l4.w);
-                        const uint32_t dst_hi = su32(hbuf) + (uint32_t)((size_t)(cur ^ 1) * L.b_bytes +
-                                                                       ((size_t)((rank * CPC + cc) * 2 + 0) * NB + bb) * 16);
-                        const uint32_t dst_lo = dst_hi + NB * 16;
-                        const uint32_t bar = su32(bar_full + (cur ^ 1));
+                        unsigned char* d = nxt + ((size_t)((rank * CPC + cc) * 2 + 0) * NR + bb) * 16;
+                        *reinterpret_cast<uint4*>(d) = h4;
+                        *reinterpret_cast<uint4*>(d + NR * 16) = l4;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");
+                    if (warp == 1) {
+                        if (ha2g_elect_one()) {
+                            const uint32_t src = su32(nxt + (size_t)rank * L.slice_bytes);
+                            const uint32_t bar = su32(bar_full + (cur ^ 1));
 #pragma unroll
-                        for (uint32_t d = 0; d < CL; ++d) {
-                            const uint32_t rbar = mapa(bar, d);
-                            st_async16(mapa(dst_hi, d), h4, rbar);
-                            st_async16(mapa(dst_lo, d), l4, rbar);
+                            for (uint32_t d = 1; d < CL; ++d) {   // nearest-rank-first order differs per CTA: no hot destination
+                                const uint32_t dst = ((uint32_t)rank + d) & (CL - 1);
+                                bulk_s2c(mapa(src, dst), src, (uint32_t)L.slice_bytes, mapa(bar, dst));
+                            }
+                            mb_arrive(bar_full + (cur ^ 1));
                         }
+                        __syncwarp();
                     }
                     if (dbg_on && tid == 32) g_dbg[s * 8 + 5] = clock64();
                 }
@@ -458,7 +509,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                 {
                     const int OR = L.orow;
                     const int narr = g_gates != nullptr ? 5 : 1;
-                    if (has_item) {
+                    if (ALIAS) asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");   // every thread is done reading G
+                    if (has_item && !(xflags & 4)) {
                         float* o = outst + (size_t)bb * OR + cc * 8;
                         reinterpret_cast<float4*>(o)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
                         reinterpret_cast<float4*>(o)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
@@ -481,7 +533,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                         if (k < co_n) {
                             const int rb = co_rb[k], f4 = co_f4[k];
                             const int bg = m0 + rb, jg = j0 + f4 * 4;
-                            if (bg < M && jg < H) {               // H % 4 == 0: a float4 is entirely valid or entirely padding
+                            if (bg < M && jg < H && !(xflags & 6)) {               // H % 4 == 0: a float4 is entirely valid or entirely padding
                                 const size_t row = (size_t)bg * T + t;
                                 const float* src = outst + (size_t)rb * OR + f4 * 4;
                                 *reinterpret_cast<float4*>(g_y + row * 2 * H + dir * H + jg) = *reinterpret_cast<const float4*>(src);
@@ -496,6 +548,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                         }
                     }
                 }
+                if (ALIAS) asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");   // staging consumed before G is rewritten
                 if (dbg_on && tid == 32) g_dbg[s * 8 + 6] = clock64();
             }
         }
@@ -510,8 +563,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
 
 }  // namespace
 
-// batch rows per cluster task for a batch of M rows: the smallest NB whose chunks fit the 16 resident clusters in one wave
-static int pick_nb(int M) { return M <= 128 ? 16 : (M <= 256 ? 32 : 48); }
 
 // 1 through *ok if the second-generation tensor-core recurrence can serve hidden size H (gate rows 3*HSP <= 128, the
 // W_hh slice fits the TMEM columns behind the accumulator, one 8-unit item per epilogue thread at every NB).
@@ -519,12 +570,48 @@ HA2G_API int ha2g_gru_tc2_supported(int H, int* ok) {
     const int HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
     const int kc = CL * HSP / 8;
     bool good = 3 * HSP <= TM && kc % 2 == 0 && A_COL + kc * 8 <= TMEM_COLS && H % 4 == 0;
-    for (int nb = 16; nb <= 48 && good; nb += 16) {
+    for (int nb : {16, 20, 32, 48, 56, 64}) {
+        if (!good) break;
         const Tc2Layout L(HSP, H, nb);
         good = (HSP / 8) * nb <= 32 * epi_warps(nb) && nb * (HSP / 4) <= 2 * 32 * epi_warps(nb) && L.total <= 227 * 1024;
     }
     *ok = good ? 1 : 0;
     return 0;
+}
+
+// How many 8-CTA clusters of the recurrence kernel the device keeps resident at once (a cluster must sit inside one GPC,
+// so this is well below SMs / 8 rounded down on a floor-swept part); cached per process.
+template <int NB>
+static int max_resident_clusters() {
+    static int cached = 0;
+    if (cached > 0) return cached;
+    const Tc2Layout L(40, 300, NB);   // every configuration asks for more than half an SM's shared memory: one CTA per SM
+    if (cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) return 16;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16 * CL); cfg.blockDim = dim3(block_threads(NB)); cfg.dynamicSmemBytes = L.total;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gru_seq_fwd_tc2_kernel<NB>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 16; }
+    cached = n;
+    return n;
+}
+
+static int g_xflags = 0;
+// timing experiments only: see Tc2Params::xflags (results are wrong with any flag set)
+HA2G_API int ha2g_gru_fwd_xflags(int flags) { g_xflags = flags; return 0; }
+
+HA2G_API int ha2g_gru_max_clusters(int* n) { *n = max_resident_clusters<48>(); return 0; }
+
+// Batch rows per cluster task for a batch of M rows: the smallest NB whose row chunks, for both directions, are all
+// resident at once.  A B200 keeps 15 of these 8-CTA clusters resident (measured, tools/gru_waves.py): a 16th cluster
+// waits for a whole sequence, i.e. doubles the kernel time -- so 7 chunks per direction is the limit of one wave.
+static int pick_nb(int M) {
+    const int per_dir = max_resident_clusters<48>() / 2;
+    for (int nb : {16, 20, 32, 48, 56, 64})
+        if ((M + nb - 1) / nb <= per_dir) return nb;
+    return 64;
 }
 
 template <int NB>
@@ -534,7 +621,8 @@ static int launch_tc2(Tc2Params& p, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) return (int)e;
     int clusters = 2 * p.n_chunks;
-    if (clusters > 16) clusters = 16;
+    const int cap = max_resident_clusters<NB>() & ~1;   // the same number of clusters per direction
+    if (clusters > cap) clusters = cap;
     gru_seq_fwd_tc2_kernel<NB><<<clusters * CL, block_threads(NB), L.total, stream>>>(p);
     HA2G_RETURN_LAST();
 }
@@ -551,7 +639,7 @@ HA2G_API int ha2g_gru_seq_fwd_tc2(const float* gi, const float* w_hh_f, const fl
     return ha2g_gru_seq_fwd_tc2_dbg(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, M_gates, T, H, 0, nullptr, stream);
 }
 
-// Same, with an explicit rows-per-cluster choice (nb = 16 / 32 / 48; 0 = automatic) and an optional device buffer dbg
+// Same, with an explicit rows-per-cluster choice (nb = 16 / 20 / 32 / 48 / 56 / 64; 0 = automatic) and an optional device buffer dbg
 // [T+1][8] of clock64() samples (cluster 0, rank 0) for phase timing:
 // 7 = MMA thread reaches the h-arrival wait, 0 = h arrived / MMA issue starts, 1 = MMAs issued + committed,
 // 2 = epilogue woken by the commit, 3 = accumulator transposed through shared memory, 4 = gate math done,
@@ -563,13 +651,17 @@ HA2G_API int ha2g_gru_seq_fwd_tc2_dbg(const float* gi, const float* w_hh_f, cons
     if (M <= 0 || T <= 0) return 0;
     Tc2Params p{};
     p.dbg = dbg;
+    p.xflags = g_xflags;
     p.gi = gi; p.w_hh[0] = w_hh_f; p.w_hh[1] = w_hh_r; p.b_hh[0] = b_hh_f; p.b_hh[1] = b_hh_r;
     p.y = y; p.gates = gates; p.M = M; p.T = T; p.H = H;
     p.M_gates = gates != nullptr ? (M_gates < M ? M_gates : M) : 0;
     p.HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
     if (nb == 0) nb = pick_nb(M);
     if (nb == 16) return launch_tc2<16>(p, stream);
+    if (nb == 20) return launch_tc2<20>(p, stream);
     if (nb == 32) return launch_tc2<32>(p, stream);
     if (nb == 48) return launch_tc2<48>(p, stream);
+    if (nb == 56) return launch_tc2<56>(p, stream);
+    if (nb == 64) return launch_tc2<64>(p, stream);
     return (int)cudaErrorInvalidValue;
 }

@@ -1,6 +1,6 @@
 // Persistent cluster GRU recurrence on tcgen05, BACKWARD (BPTT through one bidirectional layer).
 //
-// Same decomposition as the forward kernel (gru_cluster_tc2.cu): an 8-CTA cluster per (direction, 16-row batch chunk);
+// Same decomposition as the forward kernel (gru_cluster_tc2.cu): an 8-CTA cluster per (direction, NB-row batch chunk);
 // CTA `rank` owns HSP = 40 hidden units, i.e. the 3*HSP gate rows (r | z | n) of W_hh that belong to them.  Walking the
 // sequence backwards, every step does
 //   A  (epilogue warps)  dh_t of the owned units = dy_t + dh_{t+1}*z_{t+1} (carried in registers) + the 8 partial products
@@ -24,12 +24,19 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int CL = 8;          // CTAs per cluster
-constexpr int NB = 16;         // batch rows per cluster task (= UMMA N)
-constexpr int NBP = 20;        // padded row (floats) of the partial-product buffers: 80 B rows, conflict-free 128-bit stores
+// NB = batch rows per cluster task: 16, or 20 / 32 when 16-row chunks would need more clusters than the device keeps
+// resident (15 on a B200: the 16 clusters of a 128-row batch ran as two waves, i.e. at twice the time; 7 chunks of 20 rows
+// per direction fit one wave).  NN = UMMA N = NB rounded up to 16; rows NB..NN-1 of the B operand stay zero.
 constexpr int TM = 128;        // UMMA M (hidden units per M-tile)
-constexpr int TNT = 160;       // warp 0: MMA issue + TMEM alloc; warps 1-4: everything else
 constexpr int TMEM_COLS = 512;
-constexpr int A_COL = 64;      // D tiles at columns [0, 16*n_mt), W^T slices from column 64
+// padded row (floats) of the partial-product buffers: 80 / 144 B rows, conflict-free 128-bit stores
+__host__ __device__ constexpr int nbp(int NB) { return NB + 4; }
+// warp 0: MMA issue + TMEM alloc; 4 (NB = 16) or 8 (NB = 32) epilogue warps: everything else
+__host__ __device__ constexpr int epi_warps(int NB) { return NB <= 24 ? 4 : 8; }
+__host__ __device__ constexpr int mma_n(int NB) { return (NB + 15) / 16 * 16; }
+__host__ __device__ constexpr int block_threads(int NB) { return 32 + 32 * epi_warps(NB); }
+// D tiles at columns [0, NN*n_mt), W^T slices (384 columns) from column a_col
+__host__ __device__ constexpr int a_col(int NB) { return mma_n(NB) == 16 ? 64 : 128; }
 constexpr size_t MIN_SMEM = 120 * 1024;   // one CTA per SM (512-column TMEM allocation)
 
 struct BwdParams {
@@ -112,11 +119,12 @@ __device__ __forceinline__ void st8(float* p, const float* v) {
 struct BwdLayout {
     int ksteps, n_mt, orow;
     size_t bop_bytes, recv_bytes, send_bytes, slice_bytes, off_bar, off_recv, off_send, off_out, off_w, total;
-    __host__ __device__ BwdLayout(int HSP, int H) {
+    __host__ __device__ BwdLayout(int HSP, int H, int NB) {
+        const int NBP = nbp(NB);
         ksteps = (3 * HSP + 15) / 16;
         n_mt = (CL * HSP + TM - 1) / TM;
         orow = HSP + 4;
-        bop_bytes = (size_t)ksteps * 2 * 2 * NB * 16;
+        bop_bytes = (size_t)ksteps * 2 * 2 * mma_n(NB) * 16;
         slice_bytes = (size_t)HSP * NBP * 4;
         recv_bytes = (size_t)CL * slice_bytes;          // one buffer
         send_bytes = (size_t)CL * slice_bytes;          // one buffer (rows k = dst*HSP + u)
@@ -132,16 +140,19 @@ struct BwdLayout {
     }
 };
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd_tc2_kernel(BwdParams p) {
+template <int NB>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 1) gru_seq_bwd_tc2_kernel(BwdParams p) {
+    constexpr int NBP = nbp(NB), TNT = block_threads(NB), NET = 32 * epi_warps(NB), A_COL = a_col(NB), NN = mma_n(NB);
+    constexpr int CW = NB / (epi_warps(NB) / 4);   // accumulator columns (batch rows) per epilogue warp: 16 or 20
     extern __shared__ __align__(128) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int dir = cluster_id & 1;
     const int H = p.H, HSP = p.HSP, T = p.T, M = p.M;
-    const BwdLayout L(HSP, H);
+    const BwdLayout L(HSP, H, NB);
     const int KS = L.ksteps, NMT = L.n_mt, CPC = HSP / 8;
-    unsigned char* bop = smem;                                   // [2*KS chunks][hi | lo][NB][16 B]
+    unsigned char* bop = smem;                                   // [2*KS chunks][hi | lo][NN][16 B]
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* bar_recv = bar_mma + 1;                            // [2]
     uint64_t* bar_w = bar_mma + 3;
@@ -183,13 +194,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t tmem_d = tmem_base, tmem_a = tmem_base + A_COL;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
     const int et = tid - 32;
     const bool is_epi = warp >= 1;
     const int q = warp & 3;
-    const int cc = is_epi ? et / NB : 0, bb = is_epi ? et % NB : 0;
-    const bool has_item = is_epi && cc < CPC;
+    // item -> thread: the chunk index runs fastest, so that a warp's 32 items cover ~6 batch rows x the CTA's 160
+    // contiguous bytes per row of every global tensor (lanes across batch rows made every 128-bit load / store touch 32
+    // different lines and kept the load/store unit busy for ~1 500 cycles per step)
+    const int cc = is_epi ? et % CPC : 0, bb = is_epi ? et / CPC : 0;
+    const bool has_item = is_epi && bb < NB;
 
     // ---- one-time: W_hh rows of the owned gates, global -> shared (bulk copies) -> TMEM, transposed -------------------
     {
@@ -224,7 +238,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
     if (dbg_on && tid == 0) p.dbg[T * 8 + 1] = clock64();
     // A operand of M-tile mt, term (hi | lo): lane = hidden unit k = mt*128 + lane, 32-bit column ks*8 + i = the bf16 pair of
     // gate rows (kk = 16 ks + 2i, +1), kk = gate*HSP + u  <->  W_hh[gate*H + j0 + u][k]
-    if (is_epi) {
+    if (is_epi && warp <= 4) {   // one warp per TMEM lane quarter
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         for (int mt = 0; mt < NMT; ++mt) {
             const int k = mt * TM + q * 32 + lane;
@@ -253,15 +267,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (dbg_on && tid == 0) p.dbg[T * 8 + 2] = clock64();
 
-    const uint32_t lbo = 2 * NB * 16;
-    const uint64_t dbh0 = mkd(su32(bop), lbo, 128), dbl0 = mkd(su32(bop + NB * 16), lbo, 128);
+    const uint32_t lbo = 2 * NN * 16;
+    const uint64_t dbh0 = mkd(su32(bop), lbo, 128), dbl0 = mkd(su32(bop + NN * 16), lbo, 128);
     const uint64_t b_step = (uint64_t)((2 * lbo) >> 4);
     // copy-out roles for dgi / dgh (fixed per thread)
     int co_n = 0, co_rb[2] = {0, 0}, co_f4[2] = {0, 0};
     if (is_epi) {
         const int q4 = HSP / 4;
         for (int k = 0; k < 2; ++k) {
-            const int idx = et + k * 128;
+            const int idx = et + k * NET;
             if (idx < NB * q4) { co_rb[k] = idx / q4; co_f4[k] = idx % q4; co_n = k + 1; }
         }
     }
@@ -336,16 +350,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
                         uint4 h4, l4;
                         split2g(o_r[0], o_r[1], h4.x, l4.x); split2g(o_r[2], o_r[3], h4.y, l4.y);
                         split2g(o_r[4], o_r[5], h4.z, l4.z); split2g(o_r[6], o_r[7], h4.w, l4.w);
-                        *reinterpret_cast<uint4*>(bop + ((size_t)((0 * CPC + cc) * 2 + 0) * NB + bb) * 16) = h4;
-                        *reinterpret_cast<uint4*>(bop + ((size_t)((0 * CPC + cc) * 2 + 1) * NB + bb) * 16) = l4;
+                        *reinterpret_cast<uint4*>(bop + ((size_t)((0 * CPC + cc) * 2 + 0) * NN + bb) * 16) = h4;
+                        *reinterpret_cast<uint4*>(bop + ((size_t)((0 * CPC + cc) * 2 + 1) * NN + bb) * 16) = l4;
                         split2g(o_z[0], o_z[1], h4.x, l4.x); split2g(o_z[2], o_z[3], h4.y, l4.y);
                         split2g(o_z[4], o_z[5], h4.z, l4.z); split2g(o_z[6], o_z[7], h4.w, l4.w);
-                        *reinterpret_cast<uint4*>(bop + ((size_t)((1 * CPC + cc) * 2 + 0) * NB + bb) * 16) = h4;
-                        *reinterpret_cast<uint4*>(bop + ((size_t)((1 * CPC + cc) * 2 + 1) * NB + bb) * 16) = l4;
+                        *reinterpret_cast<uint4*>(bop + ((size_t)((1 * CPC + cc) * 2 + 0) * NN + bb) * 16) = h4;
+                        *reinterpret_cast<uint4*>(bop + ((size_t)((1 * CPC + cc) * 2 + 1) * NN + bb) * 16) = l4;
                         split2g(o_nr[0], o_nr[1], h4.x, l4.x); split2g(o_nr[2], o_nr[3], h4.y, l4.y);
                         split2g(o_nr[4], o_nr[5], h4.z, l4.z); split2g(o_nr[6], o_nr[7], h4.w, l4.w);
-                        *reinterpret_cast<uint4*>(bop + ((size_t)((2 * CPC + cc) * 2 + 0) * NB + bb) * 16) = h4;
-                        *reinterpret_cast<uint4*>(bop + ((size_t)((2 * CPC + cc) * 2 + 1) * NB + bb) * 16) = l4;
+                        *reinterpret_cast<uint4*>(bop + ((size_t)((2 * CPC + cc) * 2 + 0) * NN + bb) * 16) = h4;
+                        *reinterpret_cast<uint4*>(bop + ((size_t)((2 * CPC + cc) * 2 + 1) * NN + bb) * 16) = l4;
                     }
                     float* o = outst + (size_t)bb * L.orow + cc * 8;
                     const size_t as = (size_t)NB * L.orow;
@@ -357,14 +371,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
                 // ---- C: partial dh_{t-1} for all units on the tensor cores ------------------------------------------
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("bar.sync 2, 160;" ::: "memory");   // B operand written; the previous round's D has been read
+                asm volatile("bar.sync 2, %0;" ::"n"(TNT) : "memory");   // B operand written; the previous round's D has been read
                 if (warp == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (ha2g_elect_one()) {
                         for (int mt = 0; mt < NMT; ++mt) {
                             uint32_t ah = tmem_a + (uint32_t)((mt * 2 + 0) * KS * 8), al = tmem_a + (uint32_t)((mt * 2 + 1) * KS * 8);
                             uint64_t dbh = dbh0, dbl = dbl0;
-                            const uint32_t dcol = tmem_d + (uint32_t)(mt * NB);
+                            const uint32_t dcol = tmem_d + (uint32_t)(mt * NN);
                             mma16_ts(dcol, ah, dbh, idesc, 0u);
                             mma16_ts(dcol, ah, dbl, idesc, 1u);
                             mma16_ts(dcol, al, dbh, idesc, 1u);
@@ -383,7 +397,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
             }
             if (is_epi) {
                 // ---- dgi / dgh of this step to global (coalesced through the staging lines) while the MMAs run -----------
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     if (k < co_n) {
@@ -410,28 +424,33 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
                     if (dbg_on && tid == 32) p.dbg[rd * 8 + 3] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     float* sd = send + (size_t)cur * (L.send_bytes / 4);
+                    const int cg16 = ((warp - 1) >> 2) * CW;   // this warp's first accumulator column (batch row) of every tile
                     for (int mt = 0; mt < NMT; ++mt) {
                         const int k = mt * TM + q * 32 + lane;
                         if (mt * TM + q * 32 < CL * HSP) {   // warp-uniform: this lane quarter holds real units
-                            uint32_t v[16];
-                            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB);
+                            uint32_t v[20];
+                            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NN + cg16);
                             asm volatile(
                                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                                 : "r"(taddr));
+                            if (CW > 16)
+                                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]) : "r"(taddr + 16u));
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                             if (k < CL * HSP) {
-                                uint4* d4 = reinterpret_cast<uint4*>(sd + (size_t)k * NBP);
+                                uint4* d4 = reinterpret_cast<uint4*>(sd + (size_t)k * NBP + cg16);
                                 d4[0] = make_uint4(v[0], v[1], v[2], v[3]);   d4[1] = make_uint4(v[4], v[5], v[6], v[7]);
                                 d4[2] = make_uint4(v[8], v[9], v[10], v[11]); d4[3] = make_uint4(v[12], v[13], v[14], v[15]);
+                                if (CW > 16) d4[4] = make_uint4(v[16], v[17], v[18], v[19]);
                             }
                         }
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");
                     if (warp == 1) {
                         if (ha2g_elect_one()) {
                             const uint32_t dst = su32(recv) + (uint32_t)((size_t)(cur ^ 1) * L.recv_bytes + (size_t)rank * L.slice_bytes);
@@ -457,42 +476,67 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TNT, 1) gru_seq_bwd
 
 }  // namespace
 
+template <int NB>
+static bool bwd_fits(int H) {
+    const int HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
+    const BwdLayout L(HSP, H, NB);
+    return H % 4 == 0 && (HSP / 8) * NB <= 32 * epi_warps(NB) && NB * (HSP / 4) <= 2 * 32 * epi_warps(NB) &&
+           a_col(NB) + L.n_mt * 2 * L.ksteps * 8 <= TMEM_COLS && L.n_mt * mma_n(NB) <= a_col(NB) && L.total <= 227 * 1024;
+}
+
 // 1 through *ok if the tensor-core backward recurrence can serve hidden size H.
 HA2G_API int ha2g_gru_tc2_bwd_supported(int H, int* ok) {
-    const int HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
-    const BwdLayout L(HSP, H);
-    *ok = (H % 4 == 0 && (HSP / 8) * NB <= 128 && NB * (HSP / 4) <= 256 && A_COL + L.n_mt * 2 * L.ksteps * 8 <= TMEM_COLS &&
-           L.n_mt * NB <= A_COL && L.total <= 227 * 1024) ? 1 : 0;
+    *ok = (bwd_fits<16>(H) && bwd_fits<20>(H) && bwd_fits<32>(H)) ? 1 : 0;
     return 0;
 }
 
+extern "C" int ha2g_gru_max_clusters(int* n);
+
+template <int NB>
+static int launch_bwd(BwdParams& p, cudaStream_t stream) {
+    p.n_chunks = (p.M + NB - 1) / NB;
+    const BwdLayout L(p.HSP, p.H, NB);
+    cudaError_t e = cudaFuncSetAttribute(gru_seq_bwd_tc2_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) return (int)e;
+    int cap = 16;
+    ha2g_gru_max_clusters(&cap);   // resident 8-CTA clusters (one CTA per SM, like the forward kernel)
+    cap &= ~1;
+    int clusters = 2 * p.n_chunks;
+    if (clusters > cap) clusters = cap;
+    gru_seq_bwd_tc2_kernel<NB><<<clusters * CL, block_threads(NB), L.total, stream>>>(p);
+    HA2G_RETURN_LAST();
+}
+
 extern "C" int ha2g_gru_seq_bwd_tc2_dbg(const float*, int, int, const float*, const float*, const float*, const float*, float*,
-                                        float*, int, int, int, long long*, cudaStream_t);
+                                        float*, int, int, int, int, long long*, cudaStream_t);
 // All T steps of one bidirectional layer, backward, on tcgen05: writes dgi, dgh [M,T,2,3H] (gru.cu documents them) from
 // dy (element (m,t,dir,j) at dy[(m*T+t)*dy_ld + dir*dy_dir_stride + j]), y [M,T,2H] and the saved gates [M,T,2,4H].
 HA2G_API int ha2g_gru_seq_bwd_tc2(const float* dy, int dy_ld, int dy_dir_stride, const float* y, const float* gates,
                                   const float* w_hh_f, const float* w_hh_r, float* dgi, float* dgh, int M, int T, int H,
                                   cudaStream_t stream) {
-    return ha2g_gru_seq_bwd_tc2_dbg(dy, dy_ld, dy_dir_stride, y, gates, w_hh_f, w_hh_r, dgi, dgh, M, T, H, nullptr, stream);
+    return ha2g_gru_seq_bwd_tc2_dbg(dy, dy_ld, dy_dir_stride, y, gates, w_hh_f, w_hh_r, dgi, dgh, M, T, H, 0, nullptr, stream);
 }
 
-// Same, with an optional device buffer dbg [T+1][8] of clock64() samples (cluster 0, rank 0): per round 0 = saved tensors
+// Same, with an explicit rows-per-cluster choice (nb = 16 / 20 / 32; 0 = automatic: the smallest whose chunks are all resident)
+// and an optional device buffer dbg [T+1][8] of clock64() samples (cluster 0, rank 0): per round 0 = saved tensors
 // requested, 1 = partials arrived, 2 = gate gradients + B operand written, 3 = MMAs done, 4 = partials sent;
 // row T: 0 = kernel entry, 1 = W rows in shared memory, 2 = W^T in tensor memory, 3 = loop starts, 4 = loop done.
 HA2G_API int ha2g_gru_seq_bwd_tc2_dbg(const float* dy, int dy_ld, int dy_dir_stride, const float* y, const float* gates,
                                       const float* w_hh_f, const float* w_hh_r, float* dgi, float* dgh, int M, int T, int H,
-                                      long long* dbg, cudaStream_t stream) {
+                                      int nb, long long* dbg, cudaStream_t stream) {
+    if (M <= 0 || T <= 0) return 0;
     BwdParams p{};
     p.dbg = dbg;
     p.dy = dy; p.dy_ld = dy_ld; p.dy_dir_stride = dy_dir_stride; p.y = y; p.gates = gates;
     p.w_hh[0] = w_hh_f; p.w_hh[1] = w_hh_r; p.dgi = dgi; p.dgh = dgh; p.M = M; p.T = T; p.H = H;
     p.HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
-    p.n_chunks = (M + NB - 1) / NB;
-    const BwdLayout L(p.HSP, H);
-    cudaError_t e = cudaFuncSetAttribute(gru_seq_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-    if (e != cudaSuccess) return (int)e;
-    int clusters = 2 * p.n_chunks;
-    if (clusters > 16) clusters = 16;
-    gru_seq_bwd_tc2_kernel<<<clusters * CL, TNT, L.total, stream>>>(p);
-    HA2G_RETURN_LAST();
+    if (nb == 0) {
+        int cap = 16;
+        ha2g_gru_max_clusters(&cap);
+        nb = (M + 15) / 16 <= cap / 2 ? 16 : ((M + 19) / 20 <= cap / 2 ? 20 : 32);
+    }
+    if (nb == 16) return launch_bwd<16>(p, stream);
+    if (nb == 20) return launch_bwd<20>(p, stream);
+    if (nb == 32) return launch_bwd<32>(p, stream);
+    return (int)cudaErrorInvalidValue;
 }

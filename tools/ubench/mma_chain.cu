@@ -17,6 +17,11 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint3
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbw(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done)
@@ -26,11 +31,13 @@ __device__ __forceinline__ void mbw(uint64_t* bar, uint32_t parity) {
 
 struct Cfg { int N, ts, nacc, nmma, same_a; };
 
+template <int NACC>
 __global__ void __launch_bounds__(128, 1) bench(Cfg c, long long* out /* [reps][2] */, int reps) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int wu = __shfl_sync(0xffffffffu, warp, 0);
     for (int i = tid; i < 160 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(su32(&bar)));
@@ -60,25 +67,37 @@ __global__ void __launch_bounds__(128, 1) bench(Cfg c, long long* out /* [reps][
     unsigned char* a_smem = smem + 96 * 1024;
     uint32_t ph = 0;
     for (int r = 0; r < reps; ++r) {
-        if (tid == 0) {
-            long long t0 = clock64();
-            unsigned long long g0, g1;
+        if (wu == 0) {   // whole warp, converged; one elected lane issues (no per-instruction election loop in the SASS)
+          long long t0 = 0, t1 = 0; unsigned long long g0 = 0, g1 = 0;
+          if (elect_one()) {
+            t0 = clock64();
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
-            for (int i = 0; i < c.nmma; ++i) {
-                const int ks = c.same_a ? 0 : i % 19;
-                const uint32_t d = tb + (uint32_t)((i % c.nacc) * c.N);
-                const uint64_t db = mkd(su32(smem + (size_t)(i % 19) * 2 * b_lbo), b_lbo, 128);
-                if (c.ts) mma_ts(d, tb + 256 + ks * 8, db, idesc, 1u);
-                else mma_ss(d, mkd(su32(a_smem + (size_t)ks * 2 * a_lbo), a_lbo, 128), db, idesc, 1u);
+            // fully unrolled: every index below is a compile-time constant, the issue loop is MMA instructions plus one
+            // 64-bit add per descriptor (as in the recurrence kernel)
+            const uint64_t db0 = mkd(su32(smem), b_lbo, 128), da0 = mkd(su32(a_smem), a_lbo, 128);
+            const uint64_t bstep = (uint64_t)((2 * b_lbo) >> 4), astep = (uint64_t)((2 * a_lbo) >> 4);
+            const uint32_t a0 = tb + 256, dstep = (uint32_t)c.N, amul = c.same_a ? 0u : 8u;
+            if (c.ts) {
+#pragma unroll
+                for (int i = 0; i < 57; ++i)
+                    mma_ts(tb + (uint32_t)(i % NACC) * dstep, a0 + (uint32_t)(i % 19) * amul, db0 + (uint64_t)(i % 19) * bstep, idesc, 1u);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 57; ++i)
+                    mma_ss(tb + (uint32_t)(i % NACC) * dstep, da0 + (uint64_t)(i % 19) * astep, db0 + (uint64_t)(i % 19) * bstep, idesc, 1u);
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(&bar)) : "memory");
-            long long t1 = clock64();
-            mbw(&bar, ph);
+            t1 = clock64();
+          }
+          __syncwarp();
+          mbw(&bar, ph);
+          if (elect_one()) {
             long long t2 = clock64();
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
             out[r * 3 + 0] = t1 - t0;
             out[r * 3 + 1] = t2 - t0;
             out[r * 3 + 2] = (long long)(g1 - g0);
+          }
         }
         ph ^= 1;
         __syncthreads();
@@ -92,7 +111,9 @@ int main() {
     const int reps = 20;
     long long* d;
     cudaMalloc(&d, reps * 3 * sizeof(long long));
-    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bench<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bench<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     printf("| N | A in | accumulators | MMAs | issue ticks | issue+complete ticks | ns | ticks/MMA | ns/MMA |\n|---|---|---|---|---|---|---|---|---|\n");
     const int Ns[] = {16, 32, 48, 64, 96, 128, 192, 256};
     for (int same_a = 0; same_a < 2; ++same_a)
@@ -102,7 +123,9 @@ int main() {
                 if (nacc * N > 256) continue;
                 if (same_a && (nacc > 1 || !ts)) continue;
                 Cfg c{N, ts, nacc, 57, same_a};
-                bench<<<1, 128, 200 * 1024>>>(c, d, reps);
+                if (nacc == 1) bench<1><<<1, 128, 200 * 1024>>>(c, d, reps);
+                else if (nacc == 2) bench<2><<<1, 128, 200 * 1024>>>(c, d, reps);
+                else bench<4><<<1, 128, 200 * 1024>>>(c, d, reps);
                 if (cudaDeviceSynchronize() != cudaSuccess) { printf("failed N=%d ts=%d: %s\n", N, ts, cudaGetErrorString(cudaGetLastError())); return 1; }
                 long long h[reps * 3];
                 cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
