@@ -240,10 +240,10 @@ class _LinearFn(torch.autograd.Function):
             gemm(g, w, dx, None, R, K, N, N, K, K, 0, 0, 0, 0, 1)
             dx = dx.reshape(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(w)
+            dw = zeros_like(w)
             gemm(g, x2, dw, None, N, K, R, N, K, K, 1, 0, 0, 1, _split_for(R, N, K))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros((N,), device=g.device, dtype=torch.float32)
+            db = zeros((N,), g.device)
             col_sum_into(g, db)
         return dx, dw, db, None
 
@@ -384,7 +384,7 @@ class _EmbeddingFn(torch.autograd.Function):
     def backward(ctx, dout):
         (idx,) = ctx.saved_tensors
         dout = _c(dout)
-        dt = torch.zeros(ctx.tshape, device=dout.device, dtype=torch.float32)
+        dt = zeros(ctx.tshape, dout.device)
         _call("ha2g_embedding_bwd", _p(dout), _p(idx), _p(_embedding_heads(idx)), _p(dt), idx.numel(), ctx.tshape[1], _st())
         return dt, None
 
@@ -407,6 +407,67 @@ def _embedding_heads(idx: torch.Tensor) -> torch.Tensor:
 
 def clear_step_caches():
     _heads_cache.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# zero-initialised gradient buffers of a step
+# ------------------------------------------------------------------------------------------------
+# The launchers ACCUMULATE weight / bias gradients into buffers their caller has zeroed.  A training step needs ~1 400 of
+# them (most a few hundred bytes); as 1 400 fill kernels they cost ~3 ms per step.  Inside a step (begin_step .. end_step)
+# they are carved out of one slab per device that a single memset clears at the step start; outside a step, and for
+# whatever does not fit the slab, ``zeros`` is torch.zeros.
+_zslab: Dict[int, dict] = {}
+_ZSLAB_ALIGN = 256
+
+
+def begin_step(device):
+    """Step start (rng.begin_step; inside the captured graph too): per-step caches dropped, the slab of zero-initialised
+    buffers cleared up to the extent the previous steps used."""
+    clear_step_caches()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        return
+    i = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _zslab.get(i)
+    if st is None:
+        cap = int(os.environ.get("HA2G_ZERO_SLAB_MB", "1024")) << 20
+        st = _zslab[i] = {"buf": torch.empty(cap, dtype=torch.uint8, device=f"cuda:{i}") if cap > 0 else None, "cap": cap,
+                          "off": 0, "hw": 0, "clean": 0, "active": False}
+    st["off"] = 0
+    st["clean"] = st["hw"]
+    st["active"] = st["buf"] is not None
+    if st["clean"] > 0:
+        st["buf"][:st["clean"]].zero_()
+
+
+def end_step(device=None):
+    for st in _zslab.values():
+        st["active"] = False
+
+
+def zeros(shape, device, dtype=torch.float32):
+    """torch.zeros for a buffer that lives at most until the next step start (a gradient on its way to Adam)."""
+    dev = torch.device(device)
+    st = _zslab.get(dev.index if dev.index is not None else torch.cuda.current_device()) if dev.type == "cuda" else None
+    if st is None or not st["active"] or dtype != torch.float32:
+        return torch.zeros(shape, device=device, dtype=dtype)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    nbytes = (4 * n + _ZSLAB_ALIGN - 1) // _ZSLAB_ALIGN * _ZSLAB_ALIGN
+    off = st["off"]
+    if n == 0 or off + nbytes > st["cap"]:
+        return torch.zeros(shape, device=device, dtype=dtype)
+    t = st["buf"][off:off + 4 * n].view(torch.float32).view(tuple(int(d) for d in shape))
+    st["off"] = off + nbytes
+    st["hw"] = max(st["hw"], st["off"])
+    if st["off"] > st["clean"]:   # first steps (and growth): beyond what the step-start memset covered
+        t.zero_()
+    return t
+
+
+def zeros_like(x):
+    return zeros(tuple(x.shape), x.device, x.dtype)
 
 
 def embedding(table, idx):
@@ -475,7 +536,7 @@ class _ConcatSeqFn(torch.autograd.Function):
                 _call("ha2g_copy_cols", _p(dx), I, off, 1, _p(g), w, 0, 1, B * T, w, 0, _st())
                 outs.append(g)
             else:
-                g = torch.zeros((B, w), device=dx.device, dtype=torch.float32)
+                g = zeros((B, w), dx.device)
                 _call("ha2g_copy_cols", _p(dx), I, off, 1, _p(g), w, 0, T, B * T, w, 2, _st())
                 outs.append(g)
             off += w
@@ -572,10 +633,10 @@ class _BiGRUFn(torch.autograd.Function):
             I = xin.shape[2]
             # both directions' gradients of one kind live in ONE buffer: the launcher then needs a single GEMM for
             # dW_ih (dgi^T x over all 6H gate columns) and a single column sum per bias pair, and 4 zero-fills, not 8
-            gw_ih = torch.zeros((2,) + tuple(w_ih.shape), device=dev, dtype=torch.float32)
-            gw_hh = torch.zeros((2,) + tuple(w_hh.shape), device=dev, dtype=torch.float32)
-            gb_ih = torch.zeros((2,) + tuple(b_ih.shape), device=dev, dtype=torch.float32)
-            gb_hh = torch.zeros((2,) + tuple(b_hh.shape), device=dev, dtype=torch.float32)
+            gw_ih = zeros((2,) + tuple(w_ih.shape), dev)
+            gw_hh = zeros((2,) + tuple(w_hh.shape), dev)
+            gb_ih = zeros((2,) + tuple(b_ih.shape), dev)
+            gb_hh = zeros((2,) + tuple(b_hh.shape), dev)
             g = [gw_ih[0], gw_hh[0], gb_ih[0], gb_hh[0], gw_ih[1], gw_hh[1], gb_ih[1], gb_hh[1]]
             need_dx = l > 0 or ctx.needs_input_grad[0]
             dx = torch.empty((M, T, I), device=dev, dtype=torch.float32) if need_dx else None
@@ -622,8 +683,8 @@ class _TcnWeightFn(torch.autograd.Function):
         g, v, norm = ctx.saved_tensors
         O, I, Kw = v.shape
         dw = _c(dw)
-        dg = torch.zeros_like(g)
-        dv = torch.zeros_like(v)
+        dg = zeros_like(g)
+        dv = zeros_like(v)
         _call("ha2g_tcn_weight_bwd", _p(dw), _p(g), _p(v), _p(norm), _p(dg), _p(dv), O, I, Kw, _st())
         return dg, dv
 
@@ -812,8 +873,8 @@ class _BNFn(torch.autograd.Function):
         x, y, gamma, mean, invstd = ctx.saved_tensors
         dy = _c(dy)
         dx = torch.empty_like(x)
-        dg = torch.zeros_like(gamma)
-        db = torch.zeros_like(gamma)
+        dg = zeros_like(gamma)
+        db = zeros_like(gamma)
         sums = torch.empty((2 * C,), device=dy.device, dtype=torch.float64)
         _call("ha2g_bn_bwd", _p(dy), _p(x), _p(y), rows, C, pre_relu, post_act, _p(gamma), _p(mean), _p(invstd), _p(sums),
               _p(dx), _p(dg), _p(db), _st())

@@ -7,6 +7,7 @@ import torch
 import ctypes
 import os
 
+from . import ops
 from ._lib import lib
 from .ops import _c, _call, _chk, _p, _st
 
@@ -94,7 +95,7 @@ class _Conv2dFn(torch.autograd.Function):
             dx = torch.empty((N, H, W, Cin), device=dev, dtype=torch.float32)
             _call("ha2g_conv2d_dgrad", _p(dy), _p(wb), _p(dx), N, H, W, Cin, Cout, KH, KW, stride, pad, _st())
         if ctx.needs_input_grad[1]:
-            dwf = torch.zeros((KH * KW * Cin, Cout), device=dev, dtype=torch.float32)
+            dwf = ops.zeros((KH * KW * Cin, Cout), dev)
             ok2, nb2 = ctypes.c_int(0), ctypes.c_int64(0)
             if _CONV_IMPL == "tc" and stride == 1 and _WGRAD_TC and _WGRAD_IMPLICIT and dy.shape[1] == H and dy.shape[2] == W:
                 lib.ha2g_conv_wgrad_tc2_workspace(N, H, W, Cin, Cout, KH, KW, pad, ctypes.addressof(ok2), ctypes.addressof(nb2))
@@ -112,7 +113,7 @@ class _Conv2dFn(torch.autograd.Function):
             dw = torch.empty_like(w)
             _call("ha2g_conv2d_pack", _p(dwf), _p(dw), Cout, Cin, KH, KW, 2, _st())
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros((Cout,), device=dev, dtype=torch.float32)
+            db = ops.zeros((Cout,), dev)
             rows = dy.numel() // Cout
             _call("ha2g_col_sum", _p(dy), rows, Cout, Cout, _p(db), _st())
         return dx, dw, db, None, None
@@ -214,8 +215,8 @@ class _StemConvFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         N, H, W, Cout = ctx.cfg
         dy = _c(dy)
-        dw = torch.zeros((Cout, 1, 3, 3), device=dy.device, dtype=torch.float32)
-        db = torch.zeros((Cout,), device=dy.device, dtype=torch.float32)
+        dw = ops.zeros((Cout, 1, 3, 3), dy.device)
+        db = ops.zeros((Cout,), dy.device)
         _call("ha2g_stem_conv_wgrad", _p(x), _p(dy), _p(dw), _p(db), N, H, W, Cout, _st())
         return None, dw, db  # the spectrogram is an input, never differentiated
 
@@ -254,10 +255,10 @@ class _SEFn(torch.autograd.Function):
         du = torch.empty_like(u)
         ds = torch.empty((N, C), device=dev, dtype=torch.float32)
         dgap = torch.empty((N, C), device=dev, dtype=torch.float32)
-        dw1 = torch.zeros_like(w1)
-        db1 = torch.zeros((R,), device=dev, dtype=torch.float32)
-        dw2 = torch.zeros_like(w2)
-        db2 = torch.zeros((C,), device=dev, dtype=torch.float32)
+        dw1 = ops.zeros_like(w1)
+        db1 = ops.zeros((R,), dev)
+        dw2 = ops.zeros_like(w2)
+        db2 = ops.zeros((C,), dev)
         _call("ha2g_se_bwd", _p(dout), _p(out), _p(u), _p(gap), _p(h), _p(s), _p(w1), _p(w2), _p(dres), _p(du), _p(ds),
               _p(dgap), _p(dw1), _p(db1), _p(dw2), _p(db2), N, HW, C, R, _st())
         return du, dres, dw1, db1, dw2, db2

@@ -62,8 +62,8 @@ def next_call_id() -> int:
 def begin_step(device):
     """Once per training step (inside the captured graph too): tick the device-side step counter and restart the
     host-side call numbering, so a replayed graph draws fresh masks with the same baked-in call ids."""
-    from .ops import _call, _p, _st, clear_step_caches
-    clear_step_caches()
+    from .ops import _call, _p, _st, begin_step as _ops_begin_step
+    _ops_begin_step(device)
     _call("ha2g_rng_tick", _p(dropout_state(device)), _st())
     _calls[0] = 0
 

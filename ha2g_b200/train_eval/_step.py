@@ -66,7 +66,7 @@ def train_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_i
     return _finish(args, names, vals, flags)
 
 
-def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_indices, gens: List, discriminator,
+def _enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid_indices, gens: List, discriminator,
                  audio_encoder, text_encoder, gen_optimizers: List, dis_optimizer, audio_optimizer, text_optimizer,
                  adam=None):
     """Enqueue one whole step on the current stream without any host synchronisation.
@@ -206,6 +206,15 @@ def enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vid
     names = list(scalars.keys())
     packed = torch.cat([scalars[n].reshape(1) for n in names])
     return names, packed, {"use_reg": use_reg, "gan_on": gan_on, "levels": len(outs)}
+
+
+def enqueue_step(*a, **kw):
+    """Enqueue one whole step on the current stream without any host synchronisation (see _enqueue_step); closes the
+    step's zero-buffer slab (ops.begin_step opened it through rng.begin_step) whether or not the step raised."""
+    try:
+        return _enqueue_step(*a, **kw)
+    finally:
+        ops.end_step()
 
 
 def _finish(args, names, vals, flags) -> Dict[str, float]:

@@ -22,6 +22,15 @@ def _w(value: float, like: torch.Tensor) -> torch.Tensor:
 
 def train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, pose_decoder, discriminator, pose_dec_optim,
                    dis_optim) -> Dict[str, float]:
+    try:
+        return _train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, pose_decoder, discriminator,
+                               pose_dec_optim, dis_optim)
+    finally:
+        ops.end_step()   # closes the step's zero-buffer slab (opened by rng.begin_step)
+
+
+def _train_iter_gan(args, epoch, in_text, in_audio, target_poses, vid_indices, pose_decoder, discriminator, pose_dec_optim,
+                    dis_optim) -> Dict[str, float]:
     warm_up_epochs = args.loss_warmup
     dev = target_poses.device
     rng.begin_step(dev)
