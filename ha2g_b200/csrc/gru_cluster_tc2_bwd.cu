@@ -314,6 +314,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                     if (s > 0) ld8(g_y + ((size_t)b * T + tp) * 2 * H + dir * H + jbase, hp, n4);
                     ld8(g_dy + row * dy_ld + dir * dy_ds + jbase, dyv, n4);
                 }
+                // next round's saved tensors into L2 now (no registers held): their loads, issued at the top of the next
+                // round only ~1 400 cycles before first use, then pay an L2 hit instead of a DRAM round trip
+                if (live && rd + 1 < T) {
+                    const int s2 = s - 1, t2 = dir == 0 ? s2 : T - 1 - s2, tp2 = dir == 0 ? t2 - 1 : t2 + 1;
+                    const size_t row2 = (size_t)b * T + t2;
+                    const float* gs2 = g_gates + (row2 * 2 + dir) * 4 * H + jbase;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gs2));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gs2 + H));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gs2 + 2 * H));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gs2 + 3 * H));
+                    if (s2 > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(g_y + ((size_t)b * T + tp2) * 2 * H + dir * H + jbase));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g_dy + row2 * dy_ld + dir * dy_ds + jbase));
+                }
                 if (dbg_on && tid == 32) p.dbg[rd * 8 + 0] = clock64();
                 // ---- A: wait for the 8 partial products of dh_t, reduce, gate gradients ---------------------------------
                 float acc[8];

@@ -13,7 +13,9 @@ OUT = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
 WANT = {"gpu__time_duration.sum": "us", "dram__bytes_read.sum": "rd", "dram__bytes_write.sum": "wr",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pct",
         "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_pct", "launch__registers_per_thread": "regs",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "launch__grid_size": "grid"}
+        "launch__grid_size": "grid", "launch__block_size": "block", "sm__cycles_elapsed.max": "cycles",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "lsu_pct",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_wave_pct"}
 SCALE = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 
 
@@ -33,15 +35,18 @@ def read(path):
 
 def main():
     data = json.load(open(OUT)) if os.path.exists(OUT) else {}
-    print("| key | kernel | time us | DRAM read MB | DRAM write MB | DRAM % | tensor pipe % | warps active % | regs | grid |")
+    print("| key | kernel | time us | DRAM read MB | DRAM write MB | DRAM GB/s | tensor pipe % | warps active % | regs | grid x block |")
     print("|---|---|---:|---:|---:|---:|---:|---:|---:|---:|")
     for arg in sys.argv[1:]:
         key, path = arg.split("=", 1)
         m = read(path)
         data[key] = {"dram_bytes": m.get("rd", 0.0) + m.get("wr", 0.0), "dram_read": m.get("rd"), "dram_write": m.get("wr"),
                      "us": m.get("us"), "tensor_pct": m.get("tensor_pct"), "source": os.path.basename(path), "kernel": m["kernel"]}
-        print(f"| {key} | `{m['kernel'][:60]}` | {m.get('us', 0):.1f} | {m.get('rd', 0) / 1e6:.1f} | {m.get('wr', 0) / 1e6:.1f} | "
-              f"{m.get('dram_pct', 0):.1f} | {m.get('tensor_pct', 0):.1f} | {m.get('warps_pct', 0):.1f} | {m.get('regs', 0):.0f} | {m.get('grid', 0):.0f} |")
+        name = m['kernel'].replace('<unnamed>::', '').replace('void ', '').split('(')[0]
+        gbs = (m.get('rd', 0) + m.get('wr', 0)) / max(m.get('us', 1e-9), 1e-9) / 1e3
+        print(f"| {key} | `{name[:48]}` | {m.get('us', 0):.1f} | {m.get('rd', 0) / 1e6:.1f} | {m.get('wr', 0) / 1e6:.1f} | "
+              f"{gbs:.0f} | {m.get('tensor_pct', 0):.1f} | {m.get('warps_pct', 0):.1f} | {m.get('regs', 0):.0f} | "
+              f"{m.get('grid', 0):.0f} x {m.get('block', 0):.0f} |")
     json.dump(data, open(OUT, "w"), indent=1, sort_keys=True)
 
 
