@@ -45,12 +45,15 @@ constexpr int TMEM_COLS = 512; // D at columns [0,NB), W_slice hi at [64, 64+K/2
 constexpr int A_COL = 64;
 // NB = batch rows per cluster task, NN = UMMA N (>= NB, multiple of 16; accumulator columns >= NB are never read).
 // Epilogue warps (warp 0 issues the MMAs): one (8-unit chunk, batch row) gate item per thread -> 4 / 8 / 10 warps.
-__host__ __device__ constexpr int epi_warps(int NB) { return NB <= 24 ? 4 : (NB <= 48 ? 8 : 10); }
+// NH = 2: the cluster task is split into two independent halves of NB rows each, 5 epilogue warps per half (see header).
+__host__ __device__ constexpr int epi_warps(int NB, int NH = 1) { return NH == 2 ? 10 : (NB <= 24 ? 4 : (NB <= 48 ? 8 : 10)); }
 __host__ __device__ constexpr int mma_n(int NB) { return (NB + 15) / 16 * 16; }
 // accumulator columns per epilogue warp: the NB columns are split over the 1 - 3 warps that share a TMEM lane quarter, in
 // multiples of 8; this is the largest share (quarters served by 2 of the 10 warps)
-__host__ __device__ constexpr int cols_per_warp(int NB) { return ((NB + epi_warps(NB) / 4 - 1) / (epi_warps(NB) / 4) + 7) / 8 * 8; }
-__host__ __device__ constexpr int block_threads(int NB) { return 32 + 32 * epi_warps(NB); }
+__host__ __device__ constexpr int cols_per_warp(int NB, int NH = 1) {
+    return NH == 2 ? (NB + 7) / 8 * 8 : ((NB + epi_warps(NB) / 4 - 1) / (epi_warps(NB) / 4) + 7) / 8 * 8;
+}
+__host__ __device__ constexpr int block_threads(int NB, int NH = 1) { return 32 + 32 * epi_warps(NB, NH); }
 constexpr size_t MIN_SMEM = 120 * 1024;  // > half of the SM's shared memory: one CTA per SM, so the 512-column TMEM
                                          // allocation can never wait on a co-resident CTA of the same cluster
 
@@ -62,6 +65,7 @@ struct Tc2Params {
     float* gates;          // [M,T,2,4H] or nullptr
     int M, T, H, HSP, n_chunks;
     int M_gates;           // gates are stored for batch rows < M_gates only (the rows whose BPTT will run)
+    int gpt;               // > 0: every task takes gpt of the gate-storing rows and fills up with the others (see row_of)
     int xflags;            // timing experiments only (tools/time_gru_tc.py): 1 = no gi loads, 2 = no global stores, 4 = no staging
     long long* dbg;        // optional [T+1][8] clock64 samples of cluster 0 / rank 0 (phase timing), nullptr otherwise
 };
@@ -121,14 +125,15 @@ __device__ __forceinline__ void split2g(float a, float b, uint32_t& hi, uint32_t
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
-// shared memory map (bytes): barriers | tmem slot | { h[2] | G | hown | out staging }, the braces aliasing the one-time
+// shared memory map (bytes): barriers | tmem slot | { h[NH][2] | G[NH] | hown[NH] | biases }, the braces aliasing the one-time
 // fp32 staging of the CTA's W_hh rows (consumed into tensor memory before the first task starts)
 struct Tc2Layout {
     int kc;  // K chunks = CL * HSP / 8
-    size_t b_bytes, slice_bytes, off_h, off_g, off_hown, off_out, off_bias, off_bar, off_w, total;
-    int orow;   // floats per (array, batch row) line of the output staging and of hown (HSP + 4: 128-bit accesses)
+    size_t b_bytes, slice_bytes, off_h, off_g, off_hown, off_bias, off_bar, off_w, total;
+    int orow;   // floats per batch row of hown (HSP + 4: 128-bit accesses)
     int grow;   // floats per batch row of the transposed accumulator (3*HSP + 4)
-    __host__ __device__ Tc2Layout(int HSP, int H, int NB) {
+    size_t g_stride, hown_stride;   // per half (NH = 2): each half has its own G / hown / h buffers
+    __host__ __device__ Tc2Layout(int HSP, int H, int NB, int NH = 1) {
         const int NR = (NB + 7) / 8 * 8;   // rows per (chunk, hi | lo) block of the B operand: whole 8-row core matrices
         kc = CL * HSP / 8;
         b_bytes = (size_t)kc * 2 * NR * 16;
@@ -136,21 +141,14 @@ struct Tc2Layout {
         off_bar = 0;
         off_h = 128;
         off_w = 128;
-        off_g = off_h + 2 * b_bytes;
+        off_g = off_h + (size_t)NH * 2 * b_bytes;
         orow = HSP + 4;
         grow = 3 * HSP + 4;
         const size_t gsz = (size_t)NB * grow * 4, hsz = (size_t)NB * orow * 4;
-        size_t loop_end;
-        if (NB <= 48) {
-            off_hown = off_g + gsz;
-            off_out = off_hown + hsz;
-            loop_end = off_out + (size_t)5 * NB * orow * 4;   // y | r | z | n | hn lines of one step
-        } else {   // NB = 56 / 64: the output staging reuses the accumulator transpose buffer (two extra barriers per step)
-            off_out = off_g;
-            const size_t osz = (size_t)5 * NB * orow * 4;
-            off_hown = off_g + (gsz > osz ? gsz : osz);
-            loop_end = off_hown + hsz;
-        }
+        g_stride = gsz;
+        hown_stride = hsz;
+        off_hown = off_g + NH * gsz;
+        size_t loop_end = off_hown + NH * hsz;
         off_bias = loop_end;                                           // hidden-side biases of the CTA's units: [3][HSP]
         loop_end += (size_t)3 * HSP * 4;
         const size_t w_end = off_w + (size_t)3 * HSP * H * 4;          // fp32 W_hh rows of this CTA, bulk-copied once
@@ -160,37 +158,41 @@ struct Tc2Layout {
     }
 };
 
-template <int NB>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 1) gru_seq_fwd_tc2_kernel(Tc2Params p) {
-    constexpr int NEW = epi_warps(NB);          // epilogue warps
-    constexpr int TNT = block_threads(NB);
-    constexpr int NET = 32 * NEW;               // epilogue threads
+template <int NB, int NH>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB, NH), 1) gru_seq_fwd_tc2_kernel(Tc2Params p) {
+    constexpr int NEW = epi_warps(NB, NH);      // epilogue warps
+    constexpr int TNT = block_threads(NB, NH);
+    constexpr int GW = NEW / NH;                // epilogue warps per half
+    constexpr int NET = 32 * GW;                // epilogue threads per half (one named barrier per half)
     constexpr int NN = mma_n(NB);               // UMMA N (multiple of 16)
     // rows per (chunk, hi | lo) block of the B operand.  When NR < NN (NB = 20, 56) the MMA's last 8-row group reads the
     // first rows of the NEXT block: finite or not, they only reach accumulator columns >= NR, which nobody reads.
     constexpr int NR = (NB + 7) / 8 * 8;
-    constexpr int CPW = cols_per_warp(NB);      // most accumulator columns any epilogue warp handles
-    constexpr bool ALIAS = NB > 48;             // output staging aliases the transpose buffer
+    constexpr int CPW = cols_per_warp(NB, NH);  // most accumulator columns any epilogue warp handles
     extern __shared__ __align__(128) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int dir = cluster_id & 1;
     const int H = p.H, HSP = p.HSP, T = p.T, M = p.M;
-    const Tc2Layout L(HSP, H, NB);
+    const Tc2Layout L(HSP, H, NB, NH);
     const int KC = L.kc;                 // K chunks (K = 8*KC)
     const int CPC = HSP / 8;             // chunks owned per CTA
-    unsigned char* hbuf = smem + L.off_h;               // [2][KC][2][NR][16 B]
-    float* G = reinterpret_cast<float*>(smem + L.off_g);         // [NB][grow]: W_hh h of batch row b, gate rows r | z | n
-    float* hown = reinterpret_cast<float*>(smem + L.off_hown);   // [NB][orow]: fp32 master copy of the CTA's units of h
-    float* outst = reinterpret_cast<float*>(smem + L.off_out);   // [5][NB][orow]
-    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    uint64_t* bar_full = bar_mma + 1;                   // [2]: h buffer b complete (8 x slice_bytes landed)
-    uint64_t* bar_w = bar_mma + 3;                      // one-time: the W_hh rows have landed in shared memory
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
-    const float* wrows = reinterpret_cast<const float*>(smem + L.off_w);   // [3*HSP][H]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = ha2g_warp_id();   // provably warp-uniform
+    const bool is_epi = warp >= 1;
+    const int grp = is_epi ? (warp - 1) / GW : 0;       // which half of the task this epilogue warp serves
+    unsigned char* hbuf_all = smem + L.off_h;           // [NH][2][KC][2][NR][16 B]
+    unsigned char* hbuf = hbuf_all + (size_t)grp * 2 * L.b_bytes;
+    float* G = reinterpret_cast<float*>(smem + L.off_g + grp * L.g_stride);          // [NB][grow]: W_hh h of batch row b, gate rows r | z | n
+    float* hown = reinterpret_cast<float*>(smem + L.off_hown + grp * L.hown_stride); // [NB][orow]: fp32 master copy of the CTA's units of h
+    uint64_t* bar_mma_all = reinterpret_cast<uint64_t*>(smem + L.off_bar);   // [NH]: accumulator of half g complete
+    uint64_t* bar_full_all = bar_mma_all + 2;           // [NH][2]: h buffer b of half g complete (7 peer slices + own)
+    uint64_t* bar_mma = bar_mma_all + grp;
+    uint64_t* bar_full = bar_full_all + 2 * grp;
+    uint64_t* bar_w = bar_mma_all + 6;                  // one-time: the W_hh rows have landed in shared memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma_all + 7);
+    const float* wrows = reinterpret_cast<const float*>(smem + L.off_w);   // [3*HSP][H]
     const int j0 = rank * HSP;
     // kernel parameters into registers up front: indexing the by-value struct dynamically (p.w_hh[dir]) would spill it to
     // local memory and turn every global access below into a generic LD.E / ST.E behind an LDL
@@ -207,9 +209,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
     if (dbg_on && tid == 0) p.dbg[p.T * 8 + 0] = clock64();
     if (tid == 0) {
-        mbi(bar_mma, 1);
-        mbi(bar_full + 0, 2);   // arrive.expect_tx of the MMA thread + the arrival that signs off the CTA's own slice
-        mbi(bar_full + 1, 2);
+        for (int g = 0; g < NH; ++g) {
+            mbi(bar_mma_all + g, 1);
+            mbi(bar_full_all + 2 * g + 0, 2);   // arrive.expect_tx of the MMA thread + the arrival that signs off the CTA's own slice
+            mbi(bar_full_all + 2 * g + 1, 2);
+        }
         mbi(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -221,19 +225,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    const uint32_t tmem_d = tmem_base;
+    const uint32_t tmem_d = tmem_base + (uint32_t)(grp * NN);   // the half's accumulator: columns [grp*NN, grp*NN + NN)
     const uint32_t tmem_ahi = tmem_base + A_COL, tmem_alo = tmem_base + A_COL + (uint32_t)KC * 4;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
     // epilogue roles: warp -> TMEM lane quarter (warp & 3) and, with 8 warps, column half (warp - 1) / 4;
     // gate item = (chunk cc of the CTA, batch row b)
-    const int et = tid - 32;                        // 0..NET-1 for epilogue threads
-    const bool is_epi = warp >= 1;
+    const int et = tid - 32 - grp * NET;            // 0..NET-1 for the epilogue threads of a half
     const int q = warp & 3;
-    // accumulator columns of this warp: the warps w = q, q+4, q+8 <= NEW share lane quarter q and split the NB columns
-    const int nwq = q == 0 ? NEW / 4 : (NEW - q) / 4 + 1;
+    // accumulator columns of this warp: the warps of its half that share TMEM lane quarter q split the NB columns
+    int nwq = 0, iwq = 0;
+    for (int w = 1 + grp * GW; w < 1 + (grp + 1) * GW; ++w)
+        if ((w & 3) == q) { if (w < warp) ++iwq; ++nwq; }
+    if (nwq == 0) nwq = 1;
     const int cpw = ((NB + nwq - 1) / nwq + 7) / 8 * 8;
-    const int col0 = is_epi ? ((warp - 1) >> 2) * cpw : 0;   // first accumulator column of this warp
+    const int col0 = is_epi ? iwq * cpw : 0;        // first accumulator column of this warp
     // item -> thread: the chunk index runs fastest, so that a warp's 32 items cover ~6 batch rows x the CTA's 160
     // contiguous bytes per row of every global tensor (lanes across batch rows made every 128-bit load / store touch 32
     // different lines and kept the load/store unit busy for ~1 500 cycles per step)
@@ -298,8 +304,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     if (dbg_on && tid == 0) g_dbg[p.T * 8 + 2] = clock64();
     // B descriptors: chunk stride (K direction, LBO) = 2*NR*16 (hi and lo of a chunk are adjacent), 8-row groups 128 B apart
     const uint32_t lbo = 2 * NR * 16;
-    const uint64_t dbh0 = mkd(su32(hbuf), lbo, 128), dbl0 = mkd(su32(hbuf + NR * 16), lbo, 128);
-    const uint64_t dbh1 = mkd(su32(hbuf + L.b_bytes), lbo, 128), dbl1 = mkd(su32(hbuf + L.b_bytes + NR * 16), lbo, 128);
+    // (MMA warp: the descriptors of half 0; half g's buffers are 2*b_bytes further on)
+    const uint64_t dbh0 = mkd(su32(hbuf_all), lbo, 128), dbl0 = mkd(su32(hbuf_all + NR * 16), lbo, 128);
+    const uint64_t dbh1 = mkd(su32(hbuf_all + L.b_bytes), lbo, 128), dbl1 = mkd(su32(hbuf_all + L.b_bytes + NR * 16), lbo, 128);
+    const uint64_t half_step = (uint64_t)((2 * L.b_bytes) >> 4);
     const uint64_t b_step = (uint64_t)((2 * lbo) >> 4);   // one K = 16 step = two chunks
     // hidden-side biases of the CTA's units (constant over the sequence) in shared memory, [gate][HSP]: re-read as
     // broadcast 128-bit words every step rather than held in 24 registers per thread (the W_hh staging is dead by now)
@@ -309,27 +317,33 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
         bsm[e] = j < H ? b_hh[g * H + j] : 0.f;
     }
     // (made visible to the epilogue warps by the cluster.sync() that opens the first task)
-    // copy-out roles (fixed per thread; NB * HSP/4 <= 2 * NET float4 per line group)
-    int co_n = 0, co_rb[2] = {0, 0}, co_f4[2] = {0, 0};
-    if (is_epi) {
-        const int q4 = HSP / 4;
-        for (int k = 0; k < 2; ++k) {
-            const int idx = et + k * NET;
-            if (idx < NB * q4) { co_rb[k] = idx / q4; co_f4[k] = idx % q4; co_n = k + 1; }
-        }
-    }
     uint32_t it = 0;             // running step counter: phase parity of bar_mma
-    uint32_t full_ph0 = 0, full_ph1 = 0;  // phase parities of bar_full (MMA thread only)
+    uint32_t full_ph = 0;        // phase parities of bar_full[g][b], bit 2*g + b (MMA thread only)
 
     for (int task = cluster_id >> 1; task < p.n_chunks; task += n_clusters >> 1) {
-        const int m0 = task * NB;
+        // batch row of this thread's item.  Saving the gates costs 4x the store traffic of y, and only the first M_gates
+        // rows save them: with consecutive rows per task a third of the clusters would carry all of it (and set the kernel
+        // time), so every task takes gpt gate-saving rows and R - gpt of the others.
+        int brow;
+        {
+            const int R = NH * NB, i = grp * NB + bb;
+            if (p.gpt == 0) brow = task * R + i;
+            else if (i < p.gpt) brow = (task * p.gpt + i < M_gates) ? task * p.gpt + i : M;
+            else brow = M_gates + task * (R - p.gpt) + (i - p.gpt);
+            if (brow > M) brow = M;
+        }
         // h_{-1} = 0: buffer 0 (hi and lo) and the fp32 master copy; buffer 1 too, for the rows NB..NR-1 nobody writes
-        for (int e = tid; e < 2 * KC * 2 * NR; e += TNT) reinterpret_cast<uint4*>(hbuf)[e] = make_uint4(0, 0, 0, 0);
-        for (int e = tid; e < NB * L.orow; e += TNT) hown[e] = 0.f;
+        for (int e = tid; e < NH * 2 * KC * 2 * NR; e += TNT) reinterpret_cast<uint4*>(hbuf_all)[e] = make_uint4(0, 0, 0, 0);
+        {
+            float* hz = reinterpret_cast<float*>(smem + L.off_hown);
+            for (int e = tid; e < NH * NB * L.orow; e += TNT) hz[e] = 0.f;
+        }
         asm volatile("fence.proxy.async;" ::: "memory");
         if (tid == 0) {   // h_0 lands in buffer 1 (consumed by step 1), h_1 in buffer 0 (consumed by step 2)
-            if (T >= 2) mb_expect_tx(bar_full + 1, tx_bytes);
-            if (T >= 3) mb_expect_tx(bar_full + 0, tx_bytes);
+            for (int g = 0; g < NH; ++g) {
+                if (T >= 2) mb_expect_tx(bar_full_all + 2 * g + 1, tx_bytes);
+                if (T >= 3) mb_expect_tx(bar_full_all + 2 * g + 0, tx_bytes);
+            }
         }
         cluster.sync();
         if (dbg_on && tid == 0) g_dbg[p.T * 8 + 3] = clock64();
@@ -340,7 +354,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
         auto load_gi = [&](int s_next) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) gir[i] = giz[i] = gin[i] = 0.f;
-            const int b = m0 + bb;
+            const int b = brow;
             const int jbase = j0 + cc * 8;
             if (!(has_item && b < M) || s_next >= T || (xflags & 1)) return;
             const int tn = dir == 0 ? s_next : T - 1 - s_next;
@@ -366,39 +380,47 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
             const int cur = s & 1;
             // ---- tensor core: D[128 x 16] = W_slice * h_{t-1}^T ------------------------------------------------
             if (warp == 0) {   // whole warp, converged; one elected lane issues
-                if (dbg_on && lane == 0) g_dbg[s * 8 + 7] = clock64();
-                // (measured: splitting the wait into per-rank-pair barriers so that the MMAs start under the arrival of the
-                // remaining slices LOST 4-14 % -- the slices land together)
-                if (s > 0) {
-                    mbw(bar_full + cur, cur ? full_ph1 : full_ph0);
-                    if (cur) full_ph1 ^= 1; else full_ph0 ^= 1;
-                }
-                if (dbg_on && lane == 0) g_dbg[s * 8 + 0] = clock64();
-                // (the peers' slices were written by the bulk-copy engine, the own one behind a proxy fence: all visible to
-                // the tensor core's async proxy once the barrier has completed)
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (ha2g_elect_one()) {
-                    if (s > 0 && s + 2 <= T - 1) mb_expect_tx(bar_full + cur, tx_bytes);   // h_{s+1} will land here
-                    uint32_t ah = tmem_ahi, al = tmem_alo;
-                    uint64_t dbh = cur ? dbh1 : dbh0, dbl = cur ? dbl1 : dbl0;
-                    mma16_ts(tmem_d, ah, dbh, idesc, 0u);
-                    mma16_ts(tmem_d, ah, dbl, idesc, 1u);
-                    mma16_ts(tmem_d, al, dbh, idesc, 1u);
-#pragma unroll 4
-                    for (int ks = 1; ks < KC / 2; ++ks) {
-                        ah += 8; al += 8; dbh += b_step; dbl += b_step;
-                        mma16_ts(tmem_d, ah, dbh, idesc, 1u);
-                        mma16_ts(tmem_d, ah, dbl, idesc, 1u);
-                        mma16_ts(tmem_d, al, dbh, idesc, 1u);
+                // NH = 2: the halves are independent recurrences that share the weights in tensor memory.  While half g's
+                // epilogue warps do their gate math and its h travels, the tensor core works on the other half: the
+                // per-step chain (MMA -> TMEM read -> gate math -> all-gather) of one half hides under the other's.
+#pragma unroll
+                for (int g = 0; g < NH; ++g) {
+                    uint64_t* bfull = bar_full_all + 2 * g + cur;
+                    if (dbg_on && lane == 0 && g == 0) g_dbg[s * 8 + 7] = clock64();
+                    // (measured: splitting the wait into per-rank-pair barriers so that the MMAs start under the arrival of
+                    // the remaining slices LOST 4-14 % -- the slices land together)
+                    if (s > 0) {
+                        mbw(bfull, (full_ph >> (2 * g + cur)) & 1u);
+                        full_ph ^= 1u << (2 * g + cur);
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar_mma)) : "memory");
+                    if (dbg_on && lane == 0 && g == 0) g_dbg[s * 8 + 0] = clock64();
+                    // (the peers' slices were written by the bulk-copy engine, the own one behind a proxy fence: all visible
+                    // to the tensor core's async proxy once the barrier has completed)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (ha2g_elect_one()) {
+                        if (s > 0 && s + 2 <= T - 1) mb_expect_tx(bfull, tx_bytes);   // h_{s+1} will land here
+                        const uint32_t td = tmem_base + (uint32_t)(g * NN);
+                        uint32_t ah = tmem_ahi, al = tmem_alo;
+                        uint64_t dbh = (cur ? dbh1 : dbh0) + (uint64_t)g * half_step, dbl = (cur ? dbl1 : dbl0) + (uint64_t)g * half_step;
+                        mma16_ts(td, ah, dbh, idesc, 0u);
+                        mma16_ts(td, ah, dbl, idesc, 1u);
+                        mma16_ts(td, al, dbh, idesc, 1u);
+#pragma unroll 4
+                        for (int ks = 1; ks < KC / 2; ++ks) {
+                            ah += 8; al += 8; dbh += b_step; dbl += b_step;
+                            mma16_ts(td, ah, dbh, idesc, 1u);
+                            mma16_ts(td, ah, dbl, idesc, 1u);
+                            mma16_ts(td, al, dbh, idesc, 1u);
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar_mma_all + g)) : "memory");
+                    }
+                    __syncwarp();
+                    if (dbg_on && lane == 0 && g == 0) g_dbg[s * 8 + 1] = clock64();
                 }
-                __syncwarp();
-                if (dbg_on && lane == 0) g_dbg[s * 8 + 1] = clock64();
             }
             if (is_epi) {
                 // (the x-side pre-activations gir/giz/gin of this step were prefetched before the previous step's copy-out)
-                const int b = m0 + bb;
+                const int b = brow;
                 const int jbase = j0 + cc * 8;
                 const bool live = has_item && b < M;
                 mbw(bar_mma, it & 1);
@@ -427,7 +449,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");  // the epilogue warps
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NET) : "memory");  // the epilogue warps
                 if (dbg_on && tid == 32) g_dbg[s * 8 + 3] = clock64();
                 float hnew[8], sr[8], sz[8], sn[8], shn[8];
 #pragma unroll
@@ -486,8 +508,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                         *reinterpret_cast<uint4*>(d + NR * 16) = l4;
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     }
-                    asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");
-                    if (warp == 1) {
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NET) : "memory");
+                    if (warp == 1 + grp * GW) {   // the first warp of the half
                         if (ha2g_elect_one()) {
                             const uint32_t src = su32(nxt + (size_t)rank * L.slice_bytes);
                             const uint32_t bar = su32(bar_full + (cur ^ 1));
@@ -503,52 +525,31 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                     if (dbg_on && tid == 32) g_dbg[s * 8 + 5] = clock64();
                 }
                 load_gi(s + 1);   // next step's x-side pre-activations: issued before the stores below
-                // ---- y and the saved gates: off the critical path (the next step's MMA is already being fed), staged
-                // through shared memory so that the global stores are 160-byte runs instead of 32 scattered sectors per
-                // instruction (the scattered version kept the LSU busy for ~1 000 cycles per step)
-                {
-                    const int OR = L.orow;
-                    const int narr = g_gates != nullptr ? 5 : 1;
-                    if (ALIAS) asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");   // every thread is done reading G
-                    if (has_item && !(xflags & 4)) {
-                        float* o = outst + (size_t)bb * OR + cc * 8;
-                        reinterpret_cast<float4*>(o)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
-                        reinterpret_cast<float4*>(o)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
-                        if (narr == 5) {
-                            const size_t as = (size_t)NB * OR;
-                            reinterpret_cast<float4*>(o + as)[0] = make_float4(sr[0], sr[1], sr[2], sr[3]);
-                            reinterpret_cast<float4*>(o + as)[1] = make_float4(sr[4], sr[5], sr[6], sr[7]);
-                            reinterpret_cast<float4*>(o + 2 * as)[0] = make_float4(sz[0], sz[1], sz[2], sz[3]);
-                            reinterpret_cast<float4*>(o + 2 * as)[1] = make_float4(sz[4], sz[5], sz[6], sz[7]);
-                            reinterpret_cast<float4*>(o + 3 * as)[0] = make_float4(sn[0], sn[1], sn[2], sn[3]);
-                            reinterpret_cast<float4*>(o + 3 * as)[1] = make_float4(sn[4], sn[5], sn[6], sn[7]);
-                            reinterpret_cast<float4*>(o + 4 * as)[0] = make_float4(shn[0], shn[1], shn[2], shn[3]);
-                            reinterpret_cast<float4*>(o + 4 * as)[1] = make_float4(shn[4], shn[5], shn[6], shn[7]);
-                        }
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");
-                    // copy-out: thread -> up to two fixed (batch row, float4) positions of every line group
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (k < co_n) {
-                            const int rb = co_rb[k], f4 = co_f4[k];
-                            const int bg = m0 + rb, jg = j0 + f4 * 4;
-                            if (bg < M && jg < H && !(xflags & 6)) {               // H % 4 == 0: a float4 is entirely valid or entirely padding
-                                const size_t row = (size_t)bg * T + t;
-                                const float* src = outst + (size_t)rb * OR + f4 * 4;
-                                *reinterpret_cast<float4*>(g_y + row * 2 * H + dir * H + jg) = *reinterpret_cast<const float4*>(src);
-                                if (narr == 5 && bg < M_gates) {
-                                    float* gd = g_gates + (row * 2 + dir) * 4 * H + jg;
-#pragma unroll
-                                    for (int a = 1; a < 5; ++a)
-                                        *reinterpret_cast<float4*>(gd + (size_t)(a - 1) * H) =
-                                            *reinterpret_cast<const float4*>(src + (size_t)a * NB * OR);
-                                }
+                // ---- y and the saved gates: off the critical path (the next step's MMA is already being fed), straight from
+                // registers -- with the chunk-fastest item mapping the five lanes of a batch row write 160 contiguous bytes per
+                // array, which is what the shared-memory staging of the earlier versions was there to achieve
+                if (live && !(xflags & 6)) {
+                    const int n4 = (H - jbase) >= 8 ? 2 : ((H - jbase) >= 4 ? 1 : 0);   // valid float4 halves (H % 4 == 0)
+                    const size_t row = (size_t)b * T + t;
+                    if (n4 > 0) {
+                        float* yd = g_y + row * 2 * H + dir * H + jbase;
+                        reinterpret_cast<float4*>(yd)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+                        if (n4 > 1) reinterpret_cast<float4*>(yd)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
+                        if (g_gates != nullptr && b < M_gates) {
+                            float* gd = g_gates + (row * 2 + dir) * 4 * H + jbase;
+                            reinterpret_cast<float4*>(gd)[0] = make_float4(sr[0], sr[1], sr[2], sr[3]);
+                            reinterpret_cast<float4*>(gd + H)[0] = make_float4(sz[0], sz[1], sz[2], sz[3]);
+                            reinterpret_cast<float4*>(gd + 2 * H)[0] = make_float4(sn[0], sn[1], sn[2], sn[3]);
+                            reinterpret_cast<float4*>(gd + 3 * H)[0] = make_float4(shn[0], shn[1], shn[2], shn[3]);
+                            if (n4 > 1) {
+                                reinterpret_cast<float4*>(gd)[1] = make_float4(sr[4], sr[5], sr[6], sr[7]);
+                                reinterpret_cast<float4*>(gd + H)[1] = make_float4(sz[4], sz[5], sz[6], sz[7]);
+                                reinterpret_cast<float4*>(gd + 2 * H)[1] = make_float4(sn[4], sn[5], sn[6], sn[7]);
+                                reinterpret_cast<float4*>(gd + 3 * H)[1] = make_float4(shn[4], shn[5], shn[6], shn[7]);
                             }
                         }
                     }
                 }
-                if (ALIAS) asm volatile("bar.sync 1, %0;" ::"n"(NET) : "memory");   // staging consumed before G is rewritten
                 if (dbg_on && tid == 32) g_dbg[s * 8 + 6] = clock64();
             }
         }
@@ -564,36 +565,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
 }  // namespace
 
 
-// 1 through *ok if the second-generation tensor-core recurrence can serve hidden size H (gate rows 3*HSP <= 128, the
-// W_hh slice fits the TMEM columns behind the accumulator, one 8-unit item per epilogue thread at every NB).
-HA2G_API int ha2g_gru_tc2_supported(int H, int* ok) {
-    const int HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
-    const int kc = CL * HSP / 8;
-    bool good = 3 * HSP <= TM && kc % 2 == 0 && A_COL + kc * 8 <= TMEM_COLS && H % 4 == 0;
-    for (int nb : {16, 20, 32, 48, 56, 64}) {
-        if (!good) break;
-        const Tc2Layout L(HSP, H, nb);
-        good = (HSP / 8) * nb <= 32 * epi_warps(nb) && nb * (HSP / 4) <= 2 * 32 * epi_warps(nb) && L.total <= 227 * 1024;
-    }
-    *ok = good ? 1 : 0;
-    return 0;
-}
-
 // How many 8-CTA clusters of the recurrence kernel the device keeps resident at once (a cluster must sit inside one GPC,
-// so this is well below SMs / 8 rounded down on a floor-swept part); cached per process.
-template <int NB>
+// so this is well below SMs / 8 rounded down on a floor-swept part); cached per process.  Every configuration asks for
+// more than half an SM's shared memory, i.e. one CTA per SM, so one query serves them all.
 static int max_resident_clusters() {
     static int cached = 0;
     if (cached > 0) return cached;
-    const Tc2Layout L(40, 300, NB);   // every configuration asks for more than half an SM's shared memory: one CTA per SM
-    if (cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) return 16;
+    const Tc2Layout L(40, 300, 48, 1);
+    if (cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) return 16;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(16 * CL); cfg.blockDim = dim3(block_threads(NB)); cfg.dynamicSmemBytes = L.total;
+    cfg.gridDim = dim3(16 * CL); cfg.blockDim = dim3(block_threads(48, 1)); cfg.dynamicSmemBytes = L.total;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gru_seq_fwd_tc2_kernel<NB>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 16; }
+    if (cudaOccupancyMaxActiveClusters(&n, gru_seq_fwd_tc2_kernel<48, 1>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 16; }
     cached = n;
     return n;
 }
@@ -602,28 +588,51 @@ static int g_xflags = 0;
 // timing experiments only: see Tc2Params::xflags (results are wrong with any flag set)
 HA2G_API int ha2g_gru_fwd_xflags(int flags) { g_xflags = flags; return 0; }
 
-HA2G_API int ha2g_gru_max_clusters(int* n) { *n = max_resident_clusters<48>(); return 0; }
+HA2G_API int ha2g_gru_max_clusters(int* n) { *n = max_resident_clusters(); return 0; }
 
-// Batch rows per cluster task for a batch of M rows: the smallest NB whose row chunks, for both directions, are all
-// resident at once.  A B200 keeps 15 of these 8-CTA clusters resident (measured, tools/gru_waves.py): a 16th cluster
-// waits for a whole sequence, i.e. doubles the kernel time -- so 7 chunks per direction is the limit of one wave.
+// Rows per cluster task for a batch of M rows, as the code the _dbg launcher takes: the smallest task whose row chunks,
+// for both directions, are all resident at once.  A B200 keeps 15 of these 8-CTA clusters resident (measured,
+// tools/gru_waves.py): a 16th cluster waits for a whole sequence, i.e. doubles the kernel time -- so 7 chunks per
+// direction is the limit of one wave.  Tasks of 48 rows and more run as two interleaved halves (200 + rows per half).
 static int pick_nb(int M) {
-    const int per_dir = max_resident_clusters<48>() / 2;
+    const int per_dir = max_resident_clusters() / 2;
     for (int nb : {16, 20, 32, 48, 56, 64})
-        if ((M + nb - 1) / nb <= per_dir) return nb;
-    return 64;
+        if ((M + nb - 1) / nb <= per_dir) return nb >= 48 ? 200 + nb / 2 : nb;
+    return 232;
 }
 
-template <int NB>
+// 1 through *ok if the second-generation tensor-core recurrence can serve hidden size H (gate rows 3*HSP <= 128, the
+// W_hh slice fits the TMEM columns behind the accumulator, one 8-unit item per epilogue thread in every configuration).
+HA2G_API int ha2g_gru_tc2_supported(int H, int* ok) {
+    const int HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
+    const int kc = CL * HSP / 8;
+    bool good = 3 * HSP <= TM && kc % 2 == 0 && A_COL + kc * 8 <= TMEM_COLS && H % 4 == 0;
+    const int cfgs[9][2] = {{16, 1}, {20, 1}, {32, 1}, {48, 1}, {56, 1}, {64, 1}, {24, 2}, {28, 2}, {32, 2}};
+    for (int i = 0; i < 9 && good; ++i) {
+        const int nb = cfgs[i][0], nh = cfgs[i][1];
+        const Tc2Layout L(HSP, H, nb, nh);
+        const int threads_half = 32 * epi_warps(nb, nh) / nh;
+        good = (HSP / 8) * nb <= threads_half && nh * mma_n(nb) <= A_COL && L.total <= 227 * 1024;
+    }
+    *ok = good ? 1 : 0;
+    return 0;
+}
+
+template <int NB, int NH>
 static int launch_tc2(Tc2Params& p, cudaStream_t stream) {
-    p.n_chunks = (p.M + NB - 1) / NB;
-    const Tc2Layout L(p.HSP, p.H, NB);
-    cudaError_t e = cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    p.n_chunks = (p.M + NH * NB - 1) / (NH * NB);
+    p.gpt = 0;
+    if (p.M_gates > 0 && p.M_gates < p.M) {   // spread the gate-saving rows evenly over the tasks when the split works out
+        const int R = NH * NB, a = (p.M_gates + p.n_chunks - 1) / p.n_chunks;
+        if (a < R && (long long)p.n_chunks * (R - a) >= p.M - p.M_gates) p.gpt = a;
+    }
+    const Tc2Layout L(p.HSP, p.H, NB, NH);
+    cudaError_t e = cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel<NB, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) return (int)e;
     int clusters = 2 * p.n_chunks;
-    const int cap = max_resident_clusters<NB>() & ~1;   // the same number of clusters per direction
+    const int cap = max_resident_clusters() & ~1;   // the same number of clusters per direction
     if (clusters > cap) clusters = cap;
-    gru_seq_fwd_tc2_kernel<NB><<<clusters * CL, block_threads(NB), L.total, stream>>>(p);
+    gru_seq_fwd_tc2_kernel<NB, NH><<<clusters * CL, block_threads(NB, NH), L.total, stream>>>(p);
     HA2G_RETURN_LAST();
 }
 
@@ -639,7 +648,8 @@ HA2G_API int ha2g_gru_seq_fwd_tc2(const float* gi, const float* w_hh_f, const fl
     return ha2g_gru_seq_fwd_tc2_dbg(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, M_gates, T, H, 0, nullptr, stream);
 }
 
-// Same, with an explicit rows-per-cluster choice (nb = 16 / 20 / 32 / 48 / 56 / 64; 0 = automatic) and an optional device buffer dbg
+// Same, with an explicit rows-per-cluster choice (nb = 16 / 20 / 32 / 48 / 56 / 64 as one task, 224 / 228 / 232 = two
+// interleaved halves of 24 / 28 / 32 rows; 0 = automatic) and an optional device buffer dbg
 // [T+1][8] of clock64() samples (cluster 0, rank 0) for phase timing:
 // 7 = MMA thread reaches the h-arrival wait, 0 = h arrived / MMA issue starts, 1 = MMAs issued + committed,
 // 2 = epilogue woken by the commit, 3 = accumulator transposed through shared memory, 4 = gate math done,
@@ -657,11 +667,14 @@ HA2G_API int ha2g_gru_seq_fwd_tc2_dbg(const float* gi, const float* w_hh_f, cons
     p.M_gates = gates != nullptr ? (M_gates < M ? M_gates : M) : 0;
     p.HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
     if (nb == 0) nb = pick_nb(M);
-    if (nb == 16) return launch_tc2<16>(p, stream);
-    if (nb == 20) return launch_tc2<20>(p, stream);
-    if (nb == 32) return launch_tc2<32>(p, stream);
-    if (nb == 48) return launch_tc2<48>(p, stream);
-    if (nb == 56) return launch_tc2<56>(p, stream);
-    if (nb == 64) return launch_tc2<64>(p, stream);
+    if (nb == 16) return launch_tc2<16, 1>(p, stream);
+    if (nb == 20) return launch_tc2<20, 1>(p, stream);
+    if (nb == 32) return launch_tc2<32, 1>(p, stream);
+    if (nb == 48) return launch_tc2<48, 1>(p, stream);
+    if (nb == 56) return launch_tc2<56, 1>(p, stream);
+    if (nb == 64) return launch_tc2<64, 1>(p, stream);
+    if (nb == 224) return launch_tc2<24, 2>(p, stream);
+    if (nb == 228) return launch_tc2<28, 2>(p, stream);
+    if (nb == 232) return launch_tc2<32, 2>(p, stream);
     return (int)cudaErrorInvalidValue;
 }
