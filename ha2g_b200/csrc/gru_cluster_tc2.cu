@@ -254,16 +254,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB, N
         if (tid == 0 && nvalid > 0) mb_expect_tx(bar_w, (uint32_t)((size_t)nvalid * H * 4));
         __syncthreads();
         {   // rows split evenly over the 5 warps; one elected lane per warp issues its rows from uniform registers
-            const int per_warp = (3 * HSP + TNT / 32 - 1) / (TNT / 32);
-            const int r0 = warp * per_warp, r1 = min(3 * HSP, r0 + per_warp);
-            if (ha2g_elect_one()) {
-                for (int r = r0; r < r1; ++r) {
-                    const int g = r / HSP, u = r % HSP, j = j0 + u;
-                    if (j < H)
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(su32(wrows + (size_t)r * H)), "l"(W + ((size_t)g * H + j) * H), "r"((uint32_t)(H * 4)),
-                                       "r"(su32(bar_w)) : "memory");
-                }
+            // one row per thread: every thread issues its own copies, all rows in flight at once
+            for (int r = tid; r < 3 * HSP; r += TNT) {
+                const int g = r / HSP, u = r % HSP, j = j0 + u;
+                if (j < H)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(su32(wrows + (size_t)r * H)), "l"(W + ((size_t)g * H + j) * H), "r"((uint32_t)(H * 4)),
+                                   "r"(su32(bar_w)) : "memory");
             }
             __syncwarp();
         }
@@ -272,13 +269,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB, N
     }
     // shared -> TMEM: lane = gate row, 32-bit column c*4+i = the bf16 pair (k = 8c+2i, 8c+2i+1): the A-operand layout of
     // kind::f16 with A in tensor memory
-    if (is_epi && warp <= 4) {   // one warp per TMEM lane quarter
+    if (is_epi) {   // a warp can only write its own TMEM lane quarter: the warps that share a quarter split the K chunks
+        int nwa = 0, iwa = 0;
+        for (int w = 1; w <= NEW; ++w)
+            if ((w & 3) == q) { if (w < warp) ++iwa; ++nwa; }
         const int row = q * 32 + lane;
         const int g = row / HSP, u = row % HSP, j = j0 + u;
         const bool valid = g < 3 && j < H;
         const float* src = wrows + (size_t)(valid ? row : 0) * H;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        for (int c = 0; c < KC; ++c) {
+        for (int c = iwa; c < KC; c += nwa) {
             float v[8];
             if (valid && c * 8 + 7 < H) {
                 const float4 a = *reinterpret_cast<const float4*>(src + c * 8), b = *reinterpret_cast<const float4*>(src + c * 8 + 4);

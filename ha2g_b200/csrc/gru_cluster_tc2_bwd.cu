@@ -13,6 +13,9 @@
 //      cluster barrier in the loop.  Receive and staging buffers are double-buffered; a peer can only be two half-steps
 //      ahead of me after it has consumed what I sent (see the forward kernel's header for the argument).
 // Everything that depends only on saved tensors (gates, y, dy) is loaded before the wait for the partials.
+// Tried and measured no faster at B = 128 (tools/time_gru_tc.py, 133 us per layer as shipped): two interleaved half-tasks
+// of 10 rows per cluster as in the forward kernel (138 us: the chain of a half is latency- not volume-bound here, so it
+// does not get shorter with fewer rows) and a register prefetch of the saved tensors one round ahead (137 us).
 // Replaces the fp32 FMA kernel gru_seq_bwd_cluster_kernel (652 us per layer at B = 128: 19 us per step) behind
 // loss.backward() through nn.GRU, scripts/model/hierarchy_net.py:144 (H = 300) and :232 (H = 64).
 #include "common.cuh"
@@ -212,16 +215,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
         if (tid == 0 && nvalid > 0) mb_expect_tx(bar_w, (uint32_t)((size_t)nvalid * H * 4));
         __syncthreads();
         {
-            const int per_warp = (3 * HSP + TNT / 32 - 1) / (TNT / 32);
-            const int r0 = warp * per_warp, r1 = min(3 * HSP, r0 + per_warp);
-            if (ha2g_elect_one()) {
-                for (int r = r0; r < r1; ++r) {
-                    const int g = r / HSP, u = r % HSP, j = j0 + u;
-                    if (j < H)
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(su32(wrows + (size_t)r * H)), "l"(W + ((size_t)g * H + j) * H), "r"((uint32_t)(H * 4)),
-                                       "r"(su32(bar_w)) : "memory");
-                }
+            // one row per thread: every thread issues its own copies, all rows in flight at once
+            for (int r = tid; r < 3 * HSP; r += TNT) {
+                const int g = r / HSP, u = r % HSP, j = j0 + u;
+                if (j < H)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(su32(wrows + (size_t)r * H)), "l"(W + ((size_t)g * H + j) * H), "r"((uint32_t)(H * 4)),
+                                   "r"(su32(bar_w)) : "memory");
             }
             __syncwarp();
         }
