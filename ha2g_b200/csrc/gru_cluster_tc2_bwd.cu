@@ -8,8 +8,8 @@
 //      weight-gradient GEMMs) and, as bf16 hi/lo, the B operand [K = 3*HSP (pad 128) x 16] of the step's MMA;
 //   C  (one elected lane) partial dh_{t-1}[all units] = W_hh[own gate rows, :]^T * dgh_own: 3 M-tiles x 8 K-steps x 3
 //      bf16-split terms of tcgen05.mma with the transposed W_hh slice resident in TENSOR MEMORY (384 columns);
-//   D  (epilogue warps)  the [384 x 16] fp32 partial goes TMEM -> shared staging -> 8 bulk copies (3 200 B, one per owning
-//      CTA) that complete_tx on the destination's mbarrier: a reduce-scatter over distributed shared memory with no
+//   D  (epilogue warps)  the [384 x NB] fp32 partial goes TMEM -> shared staging (transposed: [owning CTA][batch row][unit],
+//      so that the receiver's reduction reads 128-bit words) -> 8 bulk copies (one slice per owning CTA) that complete_tx on the destination's mbarrier: a reduce-scatter over distributed shared memory with no
 //      cluster barrier in the loop.  Receive and staging buffers are double-buffered; a peer can only be two half-steps
 //      ahead of me after it has consumed what I sent (see the forward kernel's header for the argument).
 // Everything that depends only on saved tensors (gates, y, dy) is loaded before the wait for the partials.
@@ -32,8 +32,6 @@ constexpr int CL = 8;          // CTAs per cluster
 // per direction fit one wave).  NN = UMMA N = NB rounded up to 16; rows NB..NN-1 of the B operand stay zero.
 constexpr int TM = 128;        // UMMA M (hidden units per M-tile)
 constexpr int TMEM_COLS = 512;
-// padded row (floats) of the partial-product buffers: 80 / 144 B rows, conflict-free 128-bit stores
-__host__ __device__ constexpr int nbp(int NB) { return NB + 4; }
 // warp 0: MMA issue + TMEM alloc; 4 (NB = 16) or 8 (NB = 32) epilogue warps: everything else
 __host__ __device__ constexpr int epi_warps(int NB) { return NB <= 24 ? 4 : 8; }
 __host__ __device__ constexpr int mma_n(int NB) { return (NB + 15) / 16 * 16; }
@@ -123,12 +121,11 @@ struct BwdLayout {
     int ksteps, n_mt, orow;
     size_t bop_bytes, recv_bytes, send_bytes, slice_bytes, off_bar, off_recv, off_send, off_out, off_w, total;
     __host__ __device__ BwdLayout(int HSP, int H, int NB) {
-        const int NBP = nbp(NB);
         ksteps = (3 * HSP + 15) / 16;
         n_mt = (CL * HSP + TM - 1) / TM;
         orow = HSP + 4;
         bop_bytes = (size_t)ksteps * 2 * 2 * mma_n(NB) * 16;
-        slice_bytes = (size_t)HSP * NBP * 4;
+        slice_bytes = (size_t)NB * (HSP + 4) * 4;       // [NB batch rows][HSP units + 4]: the receiver reads 128-bit words
         recv_bytes = (size_t)CL * slice_bytes;          // one buffer
         send_bytes = (size_t)CL * slice_bytes;          // one buffer (rows k = dst*HSP + u)
         off_bar = bop_bytes;
@@ -145,8 +142,9 @@ struct BwdLayout {
 
 template <int NB>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 1) gru_seq_bwd_tc2_kernel(BwdParams p) {
-    constexpr int NBP = nbp(NB), TNT = block_threads(NB), NET = 32 * epi_warps(NB), A_COL = a_col(NB), NN = mma_n(NB);
+    constexpr int TNT = block_threads(NB), NET = 32 * epi_warps(NB), A_COL = a_col(NB), NN = mma_n(NB);
     constexpr int CW = NB / (epi_warps(NB) / 4);   // accumulator columns (batch rows) per epilogue warp: 16 or 20
+    constexpr bool RPF = epi_warps(NB) == 4;       // 5 warps per CTA: up to 255 registers per thread
     extern __shared__ __align__(128) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -160,8 +158,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
     uint64_t* bar_recv = bar_mma + 1;                            // [2]
     uint64_t* bar_w = bar_mma + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 4);
-    float* recv = reinterpret_cast<float*>(smem + L.off_recv);   // [2][CL src][HSP][NBP]
-    float* send = reinterpret_cast<float*>(smem + L.off_send);   // [2][CL*HSP][NBP]
+    float* recv = reinterpret_cast<float*>(smem + L.off_recv);   // [2][CL src][NB][orow]
+    float* send = reinterpret_cast<float*>(smem + L.off_send);   // [2][CL dst][NB][orow]
     float* outst = reinterpret_cast<float*>(smem + L.off_out);   // [4][NB][orow]: dr | dz | dn | dn*r
     const float* wrows = reinterpret_cast<const float*>(smem + L.off_w);   // [3*HSP][H], prologue only
     const int tid = threadIdx.x, lane = tid & 31;
@@ -279,6 +277,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
             if (idx < NB * q4) { co_rb[k] = idx / q4; co_f4[k] = idx % q4; co_n = k + 1; }
         }
     }
+    // D phase (fixed per thread): first accumulator column (batch row) of this warp, and where the partial of unit
+    // k = mt*128 + q*32 + lane goes inside a send buffer (slice of the owning CTA k / HSP, transposed: [batch row][unit])
+    const int OR = L.orow;
+    const int cg16 = is_epi ? ((warp - 1) >> 2) * CW : 0;
+    int sd_off[3];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt) {
+        const int k = mt * TM + q * 32 + lane;
+        sd_off[mt] = (is_epi && mt < NMT && k < CL * HSP) ? ((k / HSP) * NB + cg16) * OR + (k % HSP) : -1;
+    }
     uint32_t it = 0;                       // MMA rounds so far: phase parity of bar_mma
     uint32_t recv_ph0 = 0, recv_ph1 = 0;   // phase parities of bar_recv (tracked by every epilogue thread)
 
@@ -338,11 +346,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                     if (tid == 32 && rd + 2 <= T - 1) mb_expect_tx(bar_recv + cur, tx_bytes);
                     if (dbg_on && tid == 32) p.dbg[rd * 8 + 1] = clock64();
                     if (has_item) {
-                        const float* rb = recv + (size_t)cur * (L.recv_bytes / 4) + (size_t)(cc * 8) * NBP + bb;
+                        // batch-row-major slices: the thread's 8 units of one source are two 128-bit words (the unit-major
+                        // layout of the first version cost 64 scalar loads per thread, 5-way bank-conflicted)
+                        const float* rb = recv + (size_t)cur * (L.recv_bytes / 4) + (size_t)bb * L.orow + cc * 8;
 #pragma unroll
                         for (int src = 0; src < CL; ++src) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) acc[i] += rb[((size_t)src * HSP + i) * NBP];
+                            const float4 a0 = *reinterpret_cast<const float4*>(rb + (size_t)src * NB * L.orow);
+                            const float4 a1 = *reinterpret_cast<const float4*>(rb + (size_t)src * NB * L.orow + 4);
+                            acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+                            acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
                         }
                     }
                 }
@@ -437,28 +449,44 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(block_threads(NB), 
                     if (dbg_on && tid == 32) p.dbg[rd * 8 + 3] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     float* sd = send + (size_t)cur * (L.send_bytes / 4);
-                    const int cg16 = ((warp - 1) >> 2) * CW;   // this warp's first accumulator column (batch row) of every tile
-                    for (int mt = 0; mt < NMT; ++mt) {
-                        const int k = mt * TM + q * 32 + lane;
-                        if (mt * TM + q * 32 < CL * HSP) {   // warp-uniform: this lane quarter holds real units
-                            uint32_t v[20];
+                    // 4 epilogue warps (registers to spare): all tiles' accumulator columns into registers first (one wait),
+                    // then the transposed stores; 8 warps: tile by tile
+                    constexpr int VT = RPF ? 3 : 1, VN = CW > 16 ? 20 : 16;
+                    uint32_t v[VT][VN];
+                    auto ld_tile = [&](int mt, uint32_t* vv) {
+                        if (mt < NMT && mt * TM + q * 32 < CL * HSP) {   // warp-uniform: this lane quarter holds real units
                             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NN + cg16);
                             asm volatile(
                                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                : "=r"(vv[0]), "=r"(vv[1]), "=r"(vv[2]), "=r"(vv[3]), "=r"(vv[4]), "=r"(vv[5]), "=r"(vv[6]), "=r"(vv[7]),
+                                  "=r"(vv[8]), "=r"(vv[9]), "=r"(vv[10]), "=r"(vv[11]), "=r"(vv[12]), "=r"(vv[13]), "=r"(vv[14]), "=r"(vv[15])
                                 : "r"(taddr));
                             if (CW > 16)
                                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                             : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]) : "r"(taddr + 16u));
+                                             : "=r"(vv[VN - 4]), "=r"(vv[VN - 3]), "=r"(vv[VN - 2]), "=r"(vv[VN - 1]) : "r"(taddr + 16u));
+                        }
+                    };
+                    auto st_tile = [&](int mt, const uint32_t* vv) {
+                        if (sd_off[mt] >= 0) {   // unit k of tile mt belongs to CTA k / HSP: its partial goes into that CTA's slice, transposed
+                            float* dcol = sd + sd_off[mt];
+#pragma unroll
+                            for (int i = 0; i < VN; ++i)
+                                if (i < CW && cg16 + i < NB) dcol[i * OR] = __uint_as_float(vv[i]);
+                        }
+                    };
+                    if (RPF) {
+#pragma unroll
+                        for (int mt = 0; mt < 3; ++mt) ld_tile(mt, v[mt % VT]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int mt = 0; mt < 3; ++mt) st_tile(mt, v[mt % VT]);
+                    } else {
+#pragma unroll
+                        for (int mt = 0; mt < 3; ++mt) {
+                            ld_tile(mt, v[0]);
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                            if (k < CL * HSP) {
-                                uint4* d4 = reinterpret_cast<uint4*>(sd + (size_t)k * NBP + cg16);
-                                d4[0] = make_uint4(v[0], v[1], v[2], v[3]);   d4[1] = make_uint4(v[4], v[5], v[6], v[7]);
-                                d4[2] = make_uint4(v[8], v[9], v[10], v[11]); d4[3] = make_uint4(v[12], v[13], v[14], v[15]);
-                                if (CW > 16) d4[4] = make_uint4(v[16], v[17], v[18], v[19]);
-                            }
+                            st_tile(mt, v[0]);
                         }
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
