@@ -554,6 +554,9 @@ def main_train(a, rank, world, local_rank):
             "parity_gate": gcheck,
             "last_losses": {k: round(v, 5) for k, v in ret.items()},
             "profile_top5": sorted(((k, round(v["ms"], 3), v["calls"]) for k, v in prof.items()), key=lambda r: -r[1])[:5]}
+    if os.environ.get("HA2G_BENCH_PROFILE_ALL"):   # every launcher of one eager step (CUDA events, warm caches) -> stderr
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            print(f"  {k:34s} {v['ms']:8.3f} ms {v['calls']:5d} calls", file=sys.stderr)
     attach_cpu_baseline(a, line, world)
     print(json.dumps(line))
     _finish_process(world)

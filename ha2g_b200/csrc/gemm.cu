@@ -6,6 +6,7 @@
 // 128x64x16 tiles, 256 threads, 8x4 register micro-tile, guarded loads (any M,N,K, any stride),
 // optional split-K (per-slice partial planes + an ordered reduction: deterministic) for the skinny weight-gradient shapes.
 #include "common.cuh"
+#include <cstdio>
 
 namespace {
 
@@ -177,7 +178,14 @@ HA2G_API int ha2g_gemm_f32_kseg(const float* A, const float* B, float* C, const 
     if (M <= 0 || N <= 0) return 0;
     if (split_k < 1) split_k = 1;
     if (split_k > 1 && act != 0) return (int)cudaErrorInvalidValue;
-    if (split_k > 1) accumulate = 1;  // split-K always means C += A*B
+    if (split_k > 1) accumulate = 1;  // a caller-requested split always means C += A*B
+    // Skinny problems with a long reduction (a 128-row batch through a 4 096-wide flatten, weight gradients of narrow
+    // heads) would otherwise run their whole K loop on one or two CTAs (~20 us): split K until ~64 CTAs share it, at
+    // least 128 of K each.  Partial planes + ordered reduction, like a caller-requested split; not with a fused activation.
+    if (act == 0 && K >= 512) {
+        const int tiles = ha2g_div_up(N, BN) * ha2g_div_up(M, BM);
+        while (tiles * split_k < 64 && K / (split_k * 2) >= 128) split_k *= 2;
+    }
     int k_per = ((K + split_k - 1) / split_k + BK - 1) / BK * BK;
     if (k_per < BK) k_per = BK;
     int nz = K > 0 ? (K + k_per - 1) / k_per : 1;
@@ -213,6 +221,8 @@ extern "C" int ha2g_gemm_tc2(const float*, const float*, float*, const float*, i
                              int, int, int, int, int, cudaStream_t);
 static int g_gemm_impl = 1;
 static int g_gemm_terms = 3;
+static int g_gemm_log = 0;
+HA2G_API int ha2g_set_gemm_log(int on) { g_gemm_log = on; return 0; }
 static int gemm_impl() { return g_gemm_impl; }
 static int gemm_terms() { return g_gemm_terms; }
 HA2G_API int ha2g_set_gemm_impl(int impl) {
@@ -229,6 +239,9 @@ HA2G_API int ha2g_gemm_kseg(const float* A, const float* B, float* C, const floa
                             int kseg_stride, cudaStream_t stream) {
     const int impl = gemm_impl();
     const double flops = 2.0 * (double)M * (double)N * (double)K;
+    if (g_gemm_log)   // ha2g_set_gemm_log(1): one line per call on stderr (tools/gemm_shapes.py aggregates them)
+        fprintf(stderr, "ha2g_gemm M=%d N=%d K=%d tA=%d tB=%d act=%d acc=%d split=%d kseg=%d\n", M, N, K, transA, transB, act,
+                accumulate, split_k, kseg_len);
     // Tensor-core path (bf16 hi + lo operands: 2^-18 operand representation, ~2e-6 output error) for problems that amortise
     // the packing pass: at least two 128-row tiles of output rows, or a long reduction (the weight-gradient GEMMs: few output
     // rows, K = batch x time).  Small problems stay on the exact fp32 SIMT kernel (they gain nothing from tcgen05, and the
