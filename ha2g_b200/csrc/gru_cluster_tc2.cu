@@ -1,10 +1,13 @@
 // Persistent cluster GRU recurrence, second generation (forward) -- the fused GRU kernel of the step.
 //
-// Decomposition: an 8-CTA cluster per (direction, NB-row batch chunk).  A B200 keeps 15 such clusters resident (a cluster
-// lives inside one GPC; measured with cudaOccupancyMaxActiveClusters and tools/gru_waves.py), i.e. 7 per direction: NB is
-// the smallest of 16 / 20 / 32 / 48 / 56 / 64 whose chunks fit that one wave (the 3B = 384-row cascade of the training step
-// runs at NB = 56, a 128-row batch at NB = 20).  Until round 2 the launcher assumed 16 resident clusters: the 16th waited
-// for a whole sequence and every recurrence of the step ran at twice its one-wave time.
+// Decomposition: an 8-CTA cluster per (direction, row chunk of the batch).  A B200 keeps 15 such clusters resident (a
+// cluster lives inside one GPC; measured with cudaOccupancyMaxActiveClusters and tools/gru_waves.py), i.e. 7 per
+// direction: the rows per chunk are the smallest of 16 / 20 / 32 / 48 / 56 / 64 whose chunks fit that one wave (the
+// 3B = 384-row cascade of the training step: 56 rows; a 128-row batch: 20).  Until round 2 the launcher assumed 16 resident
+// clusters: the 16th waited for a whole sequence and every recurrence of the step ran at twice its one-wave time.
+// Chunks of 20 rows and more run as NH = 2 independent half-tasks of NB rows each inside the cluster (own accumulator
+// columns, h buffers, mbarriers and five epilogue warps per half; the MMA warp serves them alternately): the per-step
+// chain MMA -> TMEM read -> gate math -> all-gather of one half hides under the other's (384 rows: 199 -> 152 us).
 // CTA `rank` owns HSP = 40 hidden units = 3*HSP gate rows (r | z | n, zero-padded to M = 128) of W_hh for all T steps, and
 // every step computes
 //     gates^T[128 x NN] = W_slice[128 x K] * h_{t-1}^T[K x NN]          (K = 8*HSP = 320, bf16x3 split, fp32 accumulate)
@@ -593,11 +596,12 @@ HA2G_API int ha2g_gru_max_clusters(int* n) { *n = max_resident_clusters(); retur
 // Rows per cluster task for a batch of M rows, as the code the _dbg launcher takes: the smallest task whose row chunks,
 // for both directions, are all resident at once.  A B200 keeps 15 of these 8-CTA clusters resident (measured,
 // tools/gru_waves.py): a 16th cluster waits for a whole sequence, i.e. doubles the kernel time -- so 7 chunks per
-// direction is the limit of one wave.  Tasks of 48 rows and more run as two interleaved halves (200 + rows per half).
+// direction is the limit of one wave.  Tasks of 20 rows and more run as two interleaved halves (200 + rows per half):
+// measured faster at every size (128 rows: 87 vs 106 us; 224: 88 vs 115; 384: 152 vs 199).
 static int pick_nb(int M) {
     const int per_dir = max_resident_clusters() / 2;
     for (int nb : {16, 20, 32, 48, 56, 64})
-        if ((M + nb - 1) / nb <= per_dir) return nb >= 48 ? 200 + nb / 2 : nb;
+        if ((M + nb - 1) / nb <= per_dir) return nb >= 20 ? 200 + nb / 2 : nb;
     return 232;
 }
 
@@ -607,8 +611,8 @@ HA2G_API int ha2g_gru_tc2_supported(int H, int* ok) {
     const int HSP = ((H + CL - 1) / CL + 7) / 8 * 8;
     const int kc = CL * HSP / 8;
     bool good = 3 * HSP <= TM && kc % 2 == 0 && A_COL + kc * 8 <= TMEM_COLS && H % 4 == 0;
-    const int cfgs[9][2] = {{16, 1}, {20, 1}, {32, 1}, {48, 1}, {56, 1}, {64, 1}, {24, 2}, {28, 2}, {32, 2}};
-    for (int i = 0; i < 9 && good; ++i) {
+    const int cfgs[11][2] = {{16, 1}, {20, 1}, {32, 1}, {48, 1}, {56, 1}, {64, 1}, {10, 2}, {16, 2}, {24, 2}, {28, 2}, {32, 2}};
+    for (int i = 0; i < 11 && good; ++i) {
         const int nb = cfgs[i][0], nh = cfgs[i][1];
         const Tc2Layout L(HSP, H, nb, nh);
         const int threads_half = 32 * epi_warps(nb, nh) / nh;
@@ -648,8 +652,8 @@ HA2G_API int ha2g_gru_seq_fwd_tc2(const float* gi, const float* w_hh_f, const fl
     return ha2g_gru_seq_fwd_tc2_dbg(gi, w_hh_f, w_hh_r, b_hh_f, b_hh_r, y, gates, M, M_gates, T, H, 0, nullptr, stream);
 }
 
-// Same, with an explicit rows-per-cluster choice (nb = 16 / 20 / 32 / 48 / 56 / 64 as one task, 224 / 228 / 232 = two
-// interleaved halves of 24 / 28 / 32 rows; 0 = automatic) and an optional device buffer dbg
+// Same, with an explicit rows-per-cluster choice (nb = 16 / 20 / 32 / 48 / 56 / 64 as one task, 210 / 216 / 224 / 228 / 232 = two
+// interleaved halves of 10 / 16 / 24 / 28 / 32 rows; 0 = automatic) and an optional device buffer dbg
 // [T+1][8] of clock64() samples (cluster 0, rank 0) for phase timing:
 // 7 = MMA thread reaches the h-arrival wait, 0 = h arrived / MMA issue starts, 1 = MMAs issued + committed,
 // 2 = epilogue woken by the commit, 3 = accumulator transposed through shared memory, 4 = gate math done,
@@ -673,6 +677,8 @@ HA2G_API int ha2g_gru_seq_fwd_tc2_dbg(const float* gi, const float* w_hh_f, cons
     if (nb == 48) return launch_tc2<48, 1>(p, stream);
     if (nb == 56) return launch_tc2<56, 1>(p, stream);
     if (nb == 64) return launch_tc2<64, 1>(p, stream);
+    if (nb == 210) return launch_tc2<10, 2>(p, stream);
+    if (nb == 216) return launch_tc2<16, 2>(p, stream);
     if (nb == 224) return launch_tc2<24, 2>(p, stream);
     if (nb == 228) return launch_tc2<28, 2>(p, stream);
     if (nb == 232) return launch_tc2<32, 2>(p, stream);
