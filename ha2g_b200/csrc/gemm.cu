@@ -178,14 +178,7 @@ HA2G_API int ha2g_gemm_f32_kseg(const float* A, const float* B, float* C, const 
     if (M <= 0 || N <= 0) return 0;
     if (split_k < 1) split_k = 1;
     if (split_k > 1 && act != 0) return (int)cudaErrorInvalidValue;
-    if (split_k > 1) accumulate = 1;  // a caller-requested split always means C += A*B
-    // Skinny problems with a long reduction (a 128-row batch through a 4 096-wide flatten, weight gradients of narrow
-    // heads) would otherwise run their whole K loop on one or two CTAs (~20 us): split K until ~64 CTAs share it, at
-    // least 128 of K each.  Partial planes + ordered reduction, like a caller-requested split; not with a fused activation.
-    if (act == 0 && K >= 512) {
-        const int tiles = ha2g_div_up(N, BN) * ha2g_div_up(M, BM);
-        while (tiles * split_k < 64 && K / (split_k * 2) >= 128) split_k *= 2;
-    }
+    if (split_k > 1) accumulate = 1;  // split-K always means C += A*B
     int k_per = ((K + split_k - 1) / split_k + BK - 1) / BK * BK;
     if (k_per < BK) k_per = BK;
     int nz = K > 0 ? (K + k_per - 1) / k_per : 1;

@@ -7,9 +7,9 @@ run() {  # name regex invocation(0-based among matches);  ONLY="a b" restricts t
   timeout 300 ncu --set full --clock-control none --kernel-name-base demangled -k "regex:$2" -s $3 -c 1 -f -o gpurun_out/${tag}_$1 \
       python tools/profile_step.py --steps 1 > gpurun_out/${tag}_$1.log 2>&1
 }
-run gru_fwd56 "gru_seq_fwd_tc2_kernel<.int.56>" 10
+run gru_fwd28x2 "gru_seq_fwd_tc2_kernel<.int.28, .int.2>" 10
 run gru_bwd20 "gru_seq_bwd_tc2_kernel<.int.20>" 10
-run gru_fwd20 "gru_seq_fwd_tc2_kernel<.int.20>" 2
+run gru_fwd10x2 "gru_seq_fwd_tc2_kernel<.int.10, .int.2>" 2
 run gemm256 "gemm_packed_kernel<.int.256" 40
 run gemm128 "gemm_packed_kernel<.int.128" 40
 run pack_pair pack_pair_kernel 80
