@@ -33,7 +33,7 @@ def ref_gru(gi, M):
     return torch.cat(ys, 2)
 
 
-for M, nb, mg in ((128, 20, 128), (128, 210, 128), (128, 216, 128), (224, 32, 0), (224, 216, 0), (384, 0, 128)):
+for M, nb, mg in ((112, 16, 112), (128, 20, 128), (128, 0, 128), (224, 32, 0), (224, 0, 0), (336, 48, 128), (336, 0, 128), (384, 56, 128), (384, 0, 128), (1, 0, 0)):
     gi = torch.randn(M, T, 6 * H, device=dev)
     y = torch.empty(M, T, 2 * H, device=dev)
     gates = torch.full((max(mg, 1), T, 8 * H), float("nan"), device=dev)
@@ -58,7 +58,7 @@ for M, nb, mg in ((128, 20, 128), (128, 210, 128), (128, 216, 128), (224, 32, 0)
     print(f"   prologue: W->smem {int(pr[1] - pr[0])}, smem->TMEM {int(pr[2] - pr[1])}, to loop start {int(pr[3] - pr[2])}; loop {int(pr[4] - pr[3])} cycles")
 
 # ---- what-if timings (results are wrong with a flag set): where the off-critical-path work of a step goes -----------------
-for M, nb in ():
+for M, nb in ((384, 228),):
     gi = torch.randn(M, T, 6 * H, device=dev)
     y = torch.empty(M, T, 2 * H, device=dev)
     gates = torch.empty(128, T, 8 * H, device=dev)
@@ -99,7 +99,7 @@ def ref_bwd(gi, dy, M):
     return g.grad
 
 
-for M, nb in ((128, 0),):
+for M, nb in ((128, 0), (112, 16), (256, 32)):
     gi = torch.randn(M, T, 6 * H, device=dev)
     y = torch.empty(M, T, 2 * H, device=dev); gates = torch.empty(M, T, 8 * H, device=dev)
     dy = torch.randn(M, T, 2 * H, device=dev) * 0.1
