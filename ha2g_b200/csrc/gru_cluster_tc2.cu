@@ -634,7 +634,8 @@ static int launch_tc2(Tc2Params& p, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(gru_seq_fwd_tc2_kernel<NB, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) return (int)e;
     int clusters = 2 * p.n_chunks;
-    const int cap = max_resident_clusters() & ~1;   // the same number of clusters per direction
+    int cap = max_resident_clusters() & ~1;   // the same number of clusters per direction
+    if (cap < 2) cap = 2;
     if (clusters > cap) clusters = cap;
     gru_seq_fwd_tc2_kernel<NB, NH><<<clusters * CL, block_threads(NB, NH), L.total, stream>>>(p);
     HA2G_RETURN_LAST();

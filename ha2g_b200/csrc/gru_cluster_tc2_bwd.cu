@@ -542,6 +542,7 @@ static int launch_bwd(BwdParams& p, cudaStream_t stream) {
     int cap = 16;
     ha2g_gru_max_clusters(&cap);   // resident 8-CTA clusters (one CTA per SM, like the forward kernel)
     cap &= ~1;
+    if (cap < 2) cap = 2;
     int clusters = 2 * p.n_chunks;
     if (clusters > cap) clusters = cap;
     gru_seq_bwd_tc2_kernel<NB><<<clusters * CL, block_threads(NB), L.total, stream>>>(p);
