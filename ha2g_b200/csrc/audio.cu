@@ -367,7 +367,7 @@ HA2G_API int ha2g_se_fwd(const float* u, const float* res, const float* w1, cons
     if (vec) {
         int splits, px;
         se_reduce_grid(N, HW, splits, px);
-        float* part = reinterpret_cast<float*>(ha2g_ws((size_t)splits * N * C * sizeof(float)));
+        float* part = reinterpret_cast<float*>(ha2g_ws((size_t)splits * N * C * sizeof(float), stream));
         if (part == nullptr) return (int)cudaErrorMemoryAllocation;
         se_reduce_vec_kernel<0><<<dim3(splits, N), SE_NT, 0, stream>>>(reinterpret_cast<const float4*>(u), nullptr, nullptr, nullptr,
                                                                       part, HW, C, px);
@@ -395,7 +395,7 @@ HA2G_API int ha2g_se_bwd(const float* dout, const float* out, const float* u, co
     if (vec) {
         int splits, px;
         se_reduce_grid(N, HW, splits, px);
-        float* part = reinterpret_cast<float*>(ha2g_ws((size_t)splits * N * C * sizeof(float)));
+        float* part = reinterpret_cast<float*>(ha2g_ws((size_t)splits * N * C * sizeof(float), stream));
         if (part == nullptr) return (int)cudaErrorMemoryAllocation;
         se_reduce_vec_kernel<1><<<dim3(splits, N), SE_NT, 0, stream>>>(reinterpret_cast<const float4*>(u),
                                                                       reinterpret_cast<const float4*>(dout),
@@ -405,7 +405,7 @@ HA2G_API int ha2g_se_bwd(const float* dout, const float* out, const float* u, co
     } else {
         se_bwd_a_kernel<<<dim3(ha2g_div_up(C, 32), N), dim3(32, 8), 0, stream>>>(dout, out, u, dres, ds, HW, C);
     }
-    float* dz2 = reinterpret_cast<float*>(ha2g_ws((size_t)N * (C + R) * sizeof(float)));
+    float* dz2 = reinterpret_cast<float*>(ha2g_ws((size_t)N * (C + R) * sizeof(float), stream));
     if (dz2 == nullptr) return (int)cudaErrorMemoryAllocation;
     float* dz1 = dz2 + (size_t)N * C;
     se_fc_bwd_kernel<<<N, 256, 0, stream>>>(ds, s, h, gap, w1, w2, dz2, dz1, dgap, C, R);

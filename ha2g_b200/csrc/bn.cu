@@ -335,7 +335,7 @@ HA2G_API int ha2g_bn_fwd(const float* x, int64_t rows, int C, int pre_relu, int 
         const bool vec = bn_red_vec_ok(C, x, x, x);
         if (vec) bn_red_grid(rows, nparts, rows_per);
         else { bn_grid(rows, C, grid, rows_per); nparts = (int)grid.y; }
-        double* part = reinterpret_cast<double*>(ha2g_ws((size_t)nparts * 2 * C * sizeof(double)));
+        double* part = reinterpret_cast<double*>(ha2g_ws((size_t)nparts * 2 * C * sizeof(double), stream));
         if (part == nullptr) return (int)cudaErrorMemoryAllocation;
         if (vec)
             bn_reduce_vec_kernel<0><<<nparts, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), nullptr, nullptr, rows, C, pre_relu,
@@ -367,7 +367,7 @@ HA2G_API int ha2g_bn_bwd(const float* dy, const float* x, const float* y, int64_
     const bool rvec = bn_red_vec_ok(C, x, dy, post_act ? (const void*)y : (const void*)x) && bn_red_vec_ok(C, mean, invstd, x);
     if (rvec) bn_red_grid(rows, nparts, rows_per);
     else { bn_grid(rows, C, grid, rows_per); nparts = (int)grid.y; }
-    double* part = reinterpret_cast<double*>(ha2g_ws((size_t)nparts * 2 * C * sizeof(double)));
+    double* part = reinterpret_cast<double*>(ha2g_ws((size_t)nparts * 2 * C * sizeof(double), stream));
     if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     if (rvec)
         bn_reduce_vec_kernel<1><<<nparts, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy),

@@ -9,12 +9,14 @@
 #define HA2G_RETURN_LAST() \
     do { cudaError_t e__ = cudaPeekAtLastError(); return (int)e__; } while (0)
 
-// The scratch arena registered with ha2g_set_workspace (gemm_tc2.cu): nullptr when it is missing or smaller than `need`.
-// Launchers on one stream may all use it from offset 0 (stream order keeps their uses apart).
-unsigned char* ha2g_ws(size_t need_bytes);
+// The scratch arena of the stream a launcher was called on (gemm_tc2.cu): the one registered for that stream with
+// ha2g_set_workspace_lane, else the default arena of ha2g_set_workspace; nullptr when it is missing or smaller than `need`.
+// Launchers on one stream may all use their arena from offset 0 (stream order keeps their uses apart); launchers on
+// different streams run concurrently, which is why every side stream owns an arena.
+unsigned char* ha2g_ws(size_t need_bytes, cudaStream_t stream);
 // The top quarter of the same arena, reserved for the partial tiles of deterministic split-K reductions (so that a GEMM's
 // packed operands at the bottom and its partials never overlap).
-unsigned char* ha2g_ws_top(size_t need_bytes);
+unsigned char* ha2g_ws_top(size_t need_bytes, cudaStream_t stream);
 // C[m][n] = (accumulate ? C[m][n] : 0) + bias[n] + part[0][m][n] + part[1][m][n] + ...  (index order: deterministic)
 int ha2g_splitk_reduce(const float* part, int nz, int M, int N, float* C, int ldc, const float* bias, int accumulate,
                        cudaStream_t stream);

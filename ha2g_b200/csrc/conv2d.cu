@@ -413,7 +413,7 @@ HA2G_API int ha2g_conv2d_wgrad(const float* x, const float* dy, float* dwf, int 
     if (per < 256) per = 256;
     splits = (int)((P + per - 1) / per);
     dim3 grid(ha2g_div_up(Cout, bn), ha2g_div_up(Kd, CBM), splits);
-    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)splits * Kd * Cout * sizeof(float)));
+    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)splits * Kd * Cout * sizeof(float), stream));
     if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     if (bn == 64) conv2d_wgrad_kernel<64><<<grid, CNT, 0, stream>>>(x, dy, part, g, per);
     else conv2d_wgrad_kernel<32><<<grid, CNT, 0, stream>>>(x, dy, part, g, per);
@@ -444,7 +444,7 @@ HA2G_API int ha2g_stem_conv_wgrad(const float* x, const float* dy, float* dw, fl
     int64_t per = (P + ctas - 1) / ctas;
     if (per < 64) per = 64;
     ctas = (int)((P + per - 1) / per);
-    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)ctas * 10 * 32 * sizeof(float)));
+    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)ctas * 10 * 32 * sizeof(float), stream));
     if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     stem_wgrad_kernel<<<ctas, dim3(32, 8), 0, stream>>>(x, dy, part, N, H, W, Cout, per);
     stem_wgrad_reduce_kernel<<<10, 32, 0, stream>>>(part, ctas, dw, db, Cout);

@@ -291,7 +291,7 @@ HA2G_API int ha2g_conv_wgrad_tc2(const float* x, const float* dy, float* dwf, in
     dim3 grid(split, m_tiles, g.n_groups * n_tiles);
     // every pixel split writes its own [KH*KW*Cin, Cout] plane; the planes are added onto dwf in split order (deterministic)
     const int rows = KH * KW * Cin;
-    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)split * rows * Cout * sizeof(float)));
+    float* part = reinterpret_cast<float*>(ha2g_ws_top((size_t)split * rows * Cout * sizeof(float), stream));
     if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     conv_wgrad_tc2_kernel<<<grid, WNT, smem, stream>>>(reinterpret_cast<const uint4*>(xh), reinterpret_cast<const uint4*>(xl),
                                                        reinterpret_cast<const uint4*>(yh), reinterpret_cast<const uint4*>(yl),

@@ -364,7 +364,7 @@ HA2G_API int ha2g_col_sum(const float* x, int rows, int cols, int ld, float* out
     if (rows_per < 64) rows_per = 64;
     const int gy = ha2g_div_up(rows, rows_per);
     dim3 grid(gx, gy);
-    float* part = reinterpret_cast<float*>(ha2g_ws((size_t)gy * cols * sizeof(float)));
+    float* part = reinterpret_cast<float*>(ha2g_ws((size_t)gy * cols * sizeof(float), stream));
     if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     col_sum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, rows, cols, ld, part, rows_per, 0);
     col_sum_reduce_kernel<<<ha2g_div_up(cols, 128), 128, 0, stream>>>(part, gy, cols, out);

@@ -185,7 +185,7 @@ HA2G_API int ha2g_gemm_f32_kseg(const float* A, const float* B, float* C, const 
     dim3 grid(ha2g_div_up(N, BN), ha2g_div_up(M, BM), nz);
     float* part = nullptr;
     if (nz > 1) {
-        part = reinterpret_cast<float*>(ha2g_ws_top((size_t)nz * M * N * sizeof(float)));
+        part = reinterpret_cast<float*>(ha2g_ws_top((size_t)nz * M * N * sizeof(float), stream));
         if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     }
 #define LAUNCH(TA_, TB_) \

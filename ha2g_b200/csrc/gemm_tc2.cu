@@ -361,7 +361,7 @@ static int launch_packed(const void* a_hi, const void* a_lo, int rows_pa, const 
     if (e != cudaSuccess) return (int)e;
     float* part = nullptr;
     if (nz > 1) {
-        part = reinterpret_cast<float*>(ha2g_ws_top((size_t)nz * M * N * sizeof(float)));
+        part = reinterpret_cast<float*>(ha2g_ws_top((size_t)nz * M * N * sizeof(float), stream));
         if (part == nullptr) return (int)cudaErrorMemoryAllocation;
     }
     gemm_packed_kernel<BN, TERMS><<<grid, PNT, smem, stream>>>(
@@ -429,18 +429,37 @@ HA2G_API int ha2g_gemm_packed(const void* a_hi, const void* a_lo, int rows_pa, c
 // (torch-allocated) per process; calls on the same stream reuse it safely (stream order).  The launchers allocate nothing:
 // without a large enough arena they return cudaErrorMemoryAllocation.  Bottom 3/4: packed operands / reduction partials of
 // one launcher call; top 1/4: split-K partial planes.
-static unsigned char* g_ws = nullptr;
-static size_t g_ws_bytes = 0;
-static inline size_t ws_top_bytes() { return (g_ws_bytes / 4) & ~(size_t)255; }
-unsigned char* ha2g_ws(size_t need_bytes) {
-    return (g_ws != nullptr && need_bytes <= g_ws_bytes - ws_top_bytes()) ? g_ws : nullptr;
+// Scratch arenas: the default one (ha2g_set_workspace) and up to three more, each tied to one side stream
+// (ha2g_set_workspace_lane): launchers enqueued on a side stream run concurrently with the main stream's, so their operand
+// packing and partial planes must not share bytes with it.
+struct WsLane { unsigned char* ptr; size_t bytes; cudaStream_t stream; };
+static WsLane g_lanes[4] = {};
+static inline const WsLane& ws_lane(cudaStream_t stream) {
+    for (int i = 1; i < 4; ++i)
+        if (g_lanes[i].ptr != nullptr && g_lanes[i].stream == stream) return g_lanes[i];
+    return g_lanes[0];
 }
-unsigned char* ha2g_ws_top(size_t need_bytes) {
-    return (g_ws != nullptr && need_bytes <= ws_top_bytes()) ? g_ws + (g_ws_bytes - ws_top_bytes()) : nullptr;
+static inline size_t ws_top_bytes(const WsLane& l) { return (l.bytes / 4) & ~(size_t)255; }
+unsigned char* ha2g_ws(size_t need_bytes, cudaStream_t stream) {
+    const WsLane& l = ws_lane(stream);
+    return (l.ptr != nullptr && need_bytes <= l.bytes - ws_top_bytes(l)) ? l.ptr : nullptr;
+}
+unsigned char* ha2g_ws_top(size_t need_bytes, cudaStream_t stream) {
+    const WsLane& l = ws_lane(stream);
+    return (l.ptr != nullptr && need_bytes <= ws_top_bytes(l)) ? l.ptr + (l.bytes - ws_top_bytes(l)) : nullptr;
 }
 HA2G_API int ha2g_set_workspace(void* ptr, int64_t bytes) {
-    g_ws = reinterpret_cast<unsigned char*>(ptr);
-    g_ws_bytes = ptr != nullptr ? (size_t)bytes : 0;
+    g_lanes[0].ptr = reinterpret_cast<unsigned char*>(ptr);
+    g_lanes[0].bytes = ptr != nullptr ? (size_t)bytes : 0;
+    g_lanes[0].stream = nullptr;
+    return 0;
+}
+// lane 1..3: the arena of the launchers enqueued on `stream` (ptr = nullptr removes the lane)
+HA2G_API int ha2g_set_workspace_lane(int lane, void* ptr, int64_t bytes, cudaStream_t stream) {
+    if (lane < 1 || lane > 3) return (int)cudaErrorInvalidValue;
+    g_lanes[lane].ptr = reinterpret_cast<unsigned char*>(ptr);
+    g_lanes[lane].bytes = ptr != nullptr ? (size_t)bytes : 0;
+    g_lanes[lane].stream = stream;
     return 0;
 }
 
@@ -455,7 +474,7 @@ HA2G_API int ha2g_gemm_tc2(const float* A, const float* B, float* C, const float
     ha2g_pack_dims(N, K, &rpb, &cp2);
     const size_t a_bytes = (size_t)rpa * cp * 16, b_bytes = (size_t)rpb * cp * 16;
     const size_t need = 2 * (a_bytes + b_bytes);
-    unsigned char* ws = ha2g_ws(need);
+    unsigned char* ws = ha2g_ws(need, stream);
     if (ws == nullptr) return (int)cudaErrorMemoryAllocation;   // the arena (ha2g_set_workspace) is missing or too small
     unsigned char *ah = ws, *al = ws + a_bytes, *bh = ws + 2 * a_bytes, *bl = ws + 2 * a_bytes + b_bytes;
     // skinny outputs with a long reduction (e.g. the 4032->32 head projections): too few output tiles to fill 148 SMs,

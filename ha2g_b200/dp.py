@@ -110,6 +110,8 @@ def begin_backward(optimizers):
         def hook(_p, st=st):
             st["left"] -= 1
             if st["left"] == 0:
+                from . import ops
+                ops.join_side_streams()   # gradients of one optimizer may have been produced on several streams
                 _inflight[id(st["opt"])] = (_launch([q.grad for q in st["params"]], True), st["params"])
         for p in params:
             _handles.append(p.register_post_accumulate_grad_hook(hook))

@@ -6,6 +6,7 @@ CPU tensors or a missing library raise.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import List, Optional, Sequence
 
@@ -111,6 +112,62 @@ def ride_tails(head: torch.Tensor, mult: int) -> List[torch.Tensor]:
     h = head.detach()
     full = torch.as_strided(h, (B * mult, *h.shape[1:]), h.stride(), h.storage_offset())
     return [full[k * B:(k + 1) * B] for k in range(1, mult)]
+
+
+# ------------------------------------------------------------------------------------------------
+# side streams ("lanes")
+# ------------------------------------------------------------------------------------------------
+# Independent sub-graphs of the step made of small, launch-bound kernels (the six generators' text encoders) run on side
+# streams next to the main stream's work -- forward next to the audio encoder, backward (autograd replays a node on the
+# stream of its forward) next to the latency-bound GRU recurrences of the other generators.  Every side stream owns a
+# scratch arena (ha2g_set_workspace_lane): launchers pick the arena of the stream they are enqueued on.
+_lanes: Dict[int, dict] = {}
+_LANES_ON = os.environ.get("HA2G_SIDE_STREAMS", "2")
+
+
+def side_streams(device) -> List["torch.cuda.Stream"]:
+    """The side streams of `device` (created and registered with their arenas on first use); [] when disabled."""
+    n = int(_LANES_ON)
+    dev = torch.device(device)
+    if n <= 0 or dev.type != "cuda":
+        return []
+    i = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _lanes.get(i)
+    if st is None:
+        _ensure_workspace()
+        n = min(n, 3)
+        mb = int(os.environ.get("HA2G_LANE_WORKSPACE_MB", "256"))
+        st = _lanes[i] = {"streams": [torch.cuda.Stream(device=i) for _ in range(n)],
+                          "arenas": [torch.empty(mb << 20, dtype=torch.uint8, device=f"cuda:{i}") for _ in range(n)], "main": None}
+        for k, (s, a) in enumerate(zip(st["streams"], st["arenas"])):
+            lib.ha2g_set_workspace_lane(k + 1, ctypes.c_void_p(a.data_ptr()), ctypes.c_int64(a.numel()), ctypes.c_void_p(s.cuda_stream))
+    return st["streams"]
+
+
+def fork_side_streams(device) -> List["torch.cuda.Stream"]:
+    """Side streams ordered after everything enqueued so far on the current (main) stream."""
+    streams = side_streams(device)
+    if streams:
+        main = torch.cuda.current_stream(device)
+        _lanes[main.device.index]["main"] = main
+        for s in streams:
+            s.wait_stream(main)
+    return streams
+
+
+def join_side_streams(device=None):
+    """The current stream waits for the main stream and every side stream of its device (no-op without side streams):
+    called before anything that consumes results produced on several of them at once (a collective over all gradients
+    of an optimizer launched from a backward hook)."""
+    if not _lanes:
+        return
+    cur = torch.cuda.current_stream(device)
+    st = _lanes.get(cur.device.index)
+    if st is None:
+        return
+    for s in ([st["main"]] if st["main"] is not None else []) + st["streams"]:
+        if s != cur:
+            cur.wait_stream(s)
 
 
 _prof = {"on": False, "only": None, "flops_fn": None, "recs": {}}
@@ -403,6 +460,12 @@ def _embedding_heads(idx: torch.Tensor) -> torch.Tensor:
         _call("ha2g_embedding_heads", _p(idx), idx.numel(), _p(head), _st())
         hit = _heads_cache[key] = (head, idx)   # holding idx keeps its address from being recycled under the key
     return hit[0]
+
+
+def prime_embedding_heads(idx: torch.Tensor):
+    """Compute (and cache) the first-occurrence flags of `idx` now, on the current stream: backward passes on several
+    side streams then find them ready instead of racing to build them."""
+    _embedding_heads(_c(idx))
 
 
 def clear_step_caches():

@@ -78,16 +78,33 @@ def _enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vi
     dev = target.device
     rng.begin_step(dev)   # new dropout stream position for this step (device-side: valid under graph replay)
 
-    weight, feat_low, feat_mid, feat_high, linear_blend_feat = audio_encoder(in_spec, vid_indices)
-    text_feat = text_encoder(in_text_padded)
-    targets = cascade.split_targets(variant, target)
-
     scalars: Dict[str, torch.Tensor] = {}
     B, L = target.shape[0], len(gens)
     gan_on = epoch > warm_up_epochs and args.loss_gan_weight > 0.0
     use_reg = (args.z_type == "speaker" or args.z_type == "random") and args.loss_reg_weight > 0.0
     if use_reg and args.z_type != "speaker":
         raise NotImplementedError("z_type='random' is not on the hierarchy configs' path")
+    tails = (["d"] if gan_on else []) + (["r"] if use_reg else [])
+    ride = _BATCH_PASSES and len(tails) > 0 and rng.fused_dropout()
+
+    # The generators' own text encoders depend on the token batch only: with the ride-along cascade (below) they are
+    # enqueued first, on side streams, so that their many small kernels run next to the audio encoder now and -- autograd
+    # replays a node on the stream of its forward -- next to the other generators' GRU recurrences in the backward pass.
+    text_p = gen_text_feats = None
+    if ride:
+        text_p = ops.ride_pack(in_text_padded, [in_text_padded] * len(tails))
+        if ops.side_streams(dev):
+            ops.prime_embedding_heads(text_p)            # shared by every table's scatter-add: computed once, before the fork
+            side = ops.fork_side_streams(dev)
+            gen_text_feats = [None] * L
+            with ops.ride_along(1 + len(tails)):
+                for k, g in enumerate(gens):
+                    with torch.cuda.stream(side[k % len(side)]):
+                        gen_text_feats[k] = g.text_encoder(text_p)
+
+    weight, feat_low, feat_mid, feat_high, linear_blend_feat = audio_encoder(in_spec, vid_indices)
+    text_feat = text_encoder(in_text_padded)
+    targets = cascade.split_targets(variant, target)
 
     # The two cascades whose outputs the reference detaches -- the discriminator-step pass and the mismatched-speaker
     # pass of the diversity loss -- depend only on the (unchanged) generators, so they RIDE ALONG with the differentiated
@@ -95,8 +112,6 @@ def _enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vi
     # the rows per GEMM / GRU step, while autograd, the saved activations and every backward kernel only see the B rows
     # of the G-step pass.  The draws are made up front in the reference's order (D-pass noise x L, G-pass noise x L,
     # randperm, mismatched-pass noise x L).
-    tails = (["d"] if gan_on else []) + (["r"] if use_reg else [])
-    ride = _BATCH_PASSES and len(tails) > 0 and rng.fused_dropout()
     eps_g = out_r_last = z_context_rand = out_d_last = ride_result = None
     if ride:
         eps_d = [rng.randn((B, 16), dev) for _ in range(L)] if gan_on else None
@@ -106,14 +121,17 @@ def _enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vi
         m = 1 + len(tails)
         per_tail = lambda d_val, r_val: [d_val if t == "d" else r_val for t in tails]
         targets_p = [ops.ride_pack(t, per_tail(t, t)) for t in targets]
-        text_p = ops.ride_pack(in_text_padded, per_tail(in_text_padded, in_text_padded))
         blends_p = [ops.ride_pack(f, per_tail(f, f)) for f in linear_blend_feat]
         vid_p = ops.ride_pack(vid_indices, per_tail(vid_indices, rand_vids))
         eps_p = [ops.ride_pack(eps_g[k], per_tail(eps_d[k] if gan_on else None, eps_r[k] if use_reg else None))
                  for k in range(L)]
+        if gen_text_feats is not None:
+            main = torch.cuda.current_stream(dev)
+            for s_ in ops.side_streams(dev):
+                main.wait_stream(s_)
         with ops.ride_along(m):
             outs, (z_context, z_mu, z_logvar) = cascade.run_cascade(variant, gens, targets_p, text_p, blends_p, vid_p,
-                                                                    n_pre, eps=eps_p)
+                                                                    n_pre, eps=eps_p, text_feats=gen_text_feats)
         out_tails, z_tails = ops.ride_tails(outs[-1], m), ops.ride_tails(z_context, m)
         if gan_on:
             out_d_last = out_tails[tails.index("d")]
