@@ -135,13 +135,31 @@ def side_streams(device) -> List["torch.cuda.Stream"]:
     st = _lanes.get(i)
     if st is None:
         _ensure_workspace()
-        n = min(n, 3)
+        n = min(n, 2)
         mb = int(os.environ.get("HA2G_LANE_WORKSPACE_MB", "256"))
         st = _lanes[i] = {"streams": [torch.cuda.Stream(device=i) for _ in range(n)],
                           "arenas": [torch.empty(mb << 20, dtype=torch.uint8, device=f"cuda:{i}") for _ in range(n)], "main": None}
         for k, (s, a) in enumerate(zip(st["streams"], st["arenas"])):
             lib.ha2g_set_workspace_lane(k + 1, ctypes.c_void_p(a.data_ptr()), ctypes.c_int64(a.numel()), ctypes.c_void_p(s.cuda_stream))
-    return st["streams"]
+    return st.get("text", st["streams"])
+
+
+def loss_stream(device) -> Optional["torch.cuda.Stream"]:
+    """A third side stream for the contrastive losses, with an arena as large as the main one (lane 3); None when side
+    streams are disabled."""
+    if not side_streams(device) or os.environ.get("HA2G_LOSS_STREAM", "1") == "0":
+        return None
+    dev = torch.device(device)
+    i = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _lanes[i]
+    if "loss" not in st:
+        s_ = torch.cuda.Stream(device=i)
+        a_ = torch.empty(_workspace[i].numel(), dtype=torch.uint8, device=f"cuda:{i}")
+        lib.ha2g_set_workspace_lane(3, ctypes.c_void_p(a_.data_ptr()), ctypes.c_int64(a_.numel()), ctypes.c_void_p(s_.cuda_stream))
+        st["loss"], st["loss_arena"] = s_, a_
+        st["streams"] = st["streams"] + [s_]     # join_side_streams covers it
+        st["text"] = st["streams"][:-1]
+    return st["loss"]
 
 
 def fork_side_streams(device) -> List["torch.cuda.Stream"]:

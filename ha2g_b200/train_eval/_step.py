@@ -106,6 +106,24 @@ def _enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vi
     text_feat = text_encoder(in_text_padded)
     targets = cascade.split_targets(variant, target)
 
+    # The contrastive losses need the encoders' outputs only: on their own stream (with its own scratch arena -- the packed
+    # N_local x N_global coefficient matrix of the data-parallel loss is the largest tenant) they run next to the cascade,
+    # forward and backward, and so do their all-gather / reduce-scatter under data parallelism.
+    c_losses = {}
+    loss_stream = ops.loss_stream(dev) if ride else None
+
+    def contrastive_losses():
+        tf_ = text_feat.reshape(-1, text_feat.shape[2])
+        if args.loss_contrastive_pos_weight > 0.0:
+            c_losses["c_pos"] = ops_loss.contrastive(tf_, feat_high.reshape(-1, feat_high.shape[2]), variant)
+        if args.loss_contrastive_neg_weight > 0.0:  # text_low_contrastive = -criterion(...)
+            c_losses["c_neg"] = ops_loss.contrastive(tf_, feat_low.reshape(-1, feat_low.shape[2]), variant)
+
+    if loss_stream is not None:
+        loss_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(loss_stream):
+            contrastive_losses()
+
     # The two cascades whose outputs the reference detaches -- the discriminator-step pass and the mismatched-speaker
     # pass of the diversity loss -- depend only on the (unchanged) generators, so they RIDE ALONG with the differentiated
     # G-step cascade as extra batch rows (ops.ride_along): ONE cascade over 3B rows, a third of the launches, three times
@@ -170,13 +188,14 @@ def _enqueue_step(variant: str, args, epoch, in_text_padded, in_spec, target, vi
             roots.append(t)
             root_w.append(_w(w, t))
 
-    tf = text_feat.reshape(-1, text_feat.shape[2])
-    if args.loss_contrastive_pos_weight > 0.0:
-        add("c_pos", ops_loss.contrastive(tf, feat_high.reshape(-1, feat_high.shape[2]), variant),
-            args.loss_contrastive_pos_weight)
-    if args.loss_contrastive_neg_weight > 0.0:  # text_low_contrastive = -criterion(...)
-        add("c_neg", ops_loss.contrastive(tf, feat_low.reshape(-1, feat_low.shape[2]), variant),
-            -args.loss_contrastive_neg_weight)
+    if loss_stream is not None:
+        torch.cuda.current_stream(dev).wait_stream(loss_stream)
+    else:
+        contrastive_losses()
+    if "c_pos" in c_losses:
+        add("c_pos", c_losses["c_pos"], args.loss_contrastive_pos_weight)
+    if "c_neg" in c_losses:
+        add("c_neg", c_losses["c_neg"], -args.loss_contrastive_neg_weight)
 
     if ride:
         outs, z_context, z_mu, z_logvar = ride_result
