@@ -11,7 +11,8 @@
 // block of x (B, N = input-channel tile); the MMA thread issues, for every tap of its group, 4 K-steps x 3 bf16-split terms
 // into that tap's own TMEM accumulator (9 taps x 32 columns for Cin = 32; one kernel row = 3 taps x <=128 columns
 // otherwise).  x and dy are each read from HBM once (plus the halo overlap from L2); nothing 9x the activation is ever
-// written.  The epilogue adds the CTA's partial sums into dwf with fp32 atomics (split-K over pixel ranges).
+// written.  Every pixel-range split stores its partial sums into its own plane of the scratch arena; ha2g_splitk_reduce
+// adds the planes in order (deterministic).
 // Replaces conv2d_wgrad_kernel (fp32 FMA, 1.47 ms per layer-1 convolution at B = 128) and the im2col + packed-GEMM path
 // (0.65 ms per convolution, 9x activation blow-up through HBM).
 #include "common.cuh"
